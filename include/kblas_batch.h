@@ -1,0 +1,124 @@
+/*
+ * kblas_batch.h -- batched potrf / trsm / potrs / posv, uniform size.
+ *
+ * Drop-in for the hot-path subset of the reference's include/kblas_batch.h:
+ *   trsm : kblas_batch.h:773-897 (C++), 948-1053 (C)   potrf: 1380-1452, 1486-1566
+ *   potrs: kblas_batch.h:2077-2150, 2190-2278          posv : 2772-2854, 2896-2990
+ *
+ * Conventions (all inherited from the reference):
+ *  - column-major; element (i,j) of matrix b is  A[b*strideA + i + j*lda]  (strided)
+ *    or  A_array[b][i + j*lda]  (pointer array; the ARRAY lives in device memory);
+ *  - every matrix / pointer-array / info pointer is a DEVICE pointer, scalars by value;
+ *  - work is enqueued on the handle's stream, asynchronously;
+ *  - return value: KBLAS_Success (1) or a KBLAS_* error (<= 0), see kblas_defs.h;
+ *  - only uplo = 'L' (potrf/potrs/posv/trsm), diag = 'N' (trsm) and side = 'R'
+ *    (potrs/posv) are implemented, exactly as in the reference
+ *    (Xpotrf_batch_drivers.cuh:38-41, Xtrsm_batch_drivers.cuh:64-67,
+ *     Xpotrs_batch_drivers.cuh:40-43, Xposv_batch_drivers.cuh:41-44): anything else
+ *    returns KBLAS_NotImplemented;
+ *  - info_array is NOT written by default: the reference never stores a non-SPD
+ *    code (Xpotrf_batch_kernels.cuh:121-129), a non-SPD input yields NaN/Inf in the
+ *    factor.  Setting env KBLAS_B200_INFO_MODE=lapack before kblasCreate() opts in
+ *    to LAPACK semantics (info[b] = j+1 of the first non-positive pivot, else 0).
+ */
+#ifndef KBLAS_B200_BATCH_H
+#define KBLAS_B200_BATCH_H
+
+#include "kblas_defs.h"
+
+struct KBlasHandle;
+typedef struct KBlasHandle *kblasHandle_t;
+
+#ifdef __cplusplus
+/* =====================================================================================
+ * C++ API (mangled symbols, same overload set as the reference for float / double)
+ * ===================================================================================== */
+
+/* ---- workspace queries: accumulate (max) the bytes the corresponding call needs into
+ *      handle->work_space.requested_ws_state; follow with kblasAllocateWorkspace().
+ *      (reference src/workspace_queries.cu:257-266, 313-319, 340-346, 367-373) */
+void kblas_trsm_batch_wsquery        (kblasHandle_t handle, char side, int m, int n, int batchCount);
+void kblas_trsm_batch_strided_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
+void kblas_potrf_batch_wsquery        (kblasHandle_t handle, const int n, int batchCount);
+void kblas_potrf_batch_strided_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_potrs_batch_wsquery        (kblasHandle_t handle, const int m, const int n, int batchCount);
+void kblas_potrs_batch_strided_wsquery(kblasHandle_t handle, const int m, const int n, int batchCount);
+void kblas_posv_batch_wsquery        (kblasHandle_t handle, char side, const int m, const int n, int batchCount);
+void kblas_posv_batch_strided_wsquery(kblasHandle_t handle, char side, const int m, const int n, int batchCount);
+
+#define KBLAS_B200_DECL_CPP(T)                                                              \
+  /* op(A) X = alpha B (side L) or X op(A) = alpha B (side R); X overwrites B */            \
+  int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,   \
+                       const int m, const int n, const T alpha,                             \
+                       const T **A, int lda, T **B, int ldb, int batchCount);               \
+  int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,   \
+                       const int m, const int n, const T alpha,                             \
+                       const T *A, int lda, long strideA,                                   \
+                       T *B, int ldb, long strideB, int batchCount);                        \
+  /* A = L L^T in place, lower */                                                           \
+  int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n,                       \
+                        T **A, int lda, int batchCount, int *info_array);                   \
+  int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n,                       \
+                        T *A, int lda, long strideA, int batchCount, int *info_array);      \
+  /* X (L L^T) = B, B is m x n, A is the n x n factor (side R) */                           \
+  int kblas_potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
+                        const T **A, int lda, T **B, int ldb, int batchCount);              \
+  int kblas_potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
+                        const T *A, int lda, long strideA,                                  \
+                        T *B, int ldb, long strideB, int batchCount);                       \
+  /* potrf(A) then potrs(A, B) */                                                           \
+  int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
+                       T **A, int lda, T **B, int ldb, int batchCount, int *info_array);    \
+  int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
+                       T *A, int lda, long strideA, T *B, int ldb, long strideB,            \
+                       int batchCount, int *info_array);
+
+KBLAS_B200_DECL_CPP(float)
+KBLAS_B200_DECL_CPP(double)
+#undef KBLAS_B200_DECL_CPP
+
+extern "C" {
+#endif /* __cplusplus */
+
+/* =====================================================================================
+ * C API (unmangled): kblas{S,D}<op>_batch[_strided]
+ * ===================================================================================== */
+#define KBLAS_B200_DECL_C(P, T)                                                             \
+  int kblas##P##trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,\
+                           const int m, const int n, const T alpha,                         \
+                           const T **A, int lda, T **B, int ldb, int batchCount);           \
+  int kblas##P##trsm_batch_strided(kblasHandle_t handle, char side, char uplo, char trans,  \
+                           char diag, const int m, const int n, const T alpha,              \
+                           const T *A, int lda, long strideA,                               \
+                           T *B, int ldb, long strideB, int batchCount);                    \
+  int kblas##P##potrf_batch(kblasHandle_t handle, char uplo, const int n,                   \
+                           T **A, int lda, int batchCount, int *info_array);                \
+  int kblas##P##potrf_batch_strided(kblasHandle_t handle, char uplo, const int n,           \
+                           T *A, int lda, long strideA, int batchCount, int *info_array);   \
+  int kblas##P##potrs_batch(kblasHandle_t handle, char side, char uplo,                     \
+                           const int m, const int n,                                        \
+                           const T **A, int lda, T **B, int ldb, int batchCount);           \
+  int kblas##P##potrs_batch_strided(kblasHandle_t handle, char side, char uplo,             \
+                           const int m, const int n,                                        \
+                           const T *A, int lda, long strideA,                               \
+                           T *B, int ldb, long strideB, int batchCount);                    \
+  int kblas##P##posv_batch(kblasHandle_t handle, char side, char uplo,                      \
+                           const int m, const int n,                                        \
+                           T **A, int lda, T **B, int ldb, int batchCount, int *info_array);\
+  int kblas##P##posv_batch_strided(kblasHandle_t handle, char side, char uplo,              \
+                           const int m, const int n,                                        \
+                           T *A, int lda, long strideA, T *B, int ldb, long strideB,        \
+                           int batchCount, int *info_array);
+
+KBLAS_B200_DECL_C(S, float)
+KBLAS_B200_DECL_C(D, double)
+#undef KBLAS_B200_DECL_C
+
+/** ceil(x / y) * y   (reference src/kblas_common.cu:257-260) */
+int kblas_roundup(int x, int y);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* KBLAS_B200_BATCH_H */

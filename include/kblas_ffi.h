@@ -1,0 +1,88 @@
+/*
+ * kblas_ffi.h -- the complete C ABI of libkblas-gpu.so (plain C, no CUDA headers needed).
+ *
+ * This is the boundary a foreign-function binding (ctypes, cgo, JNI, N-API ...) binds.
+ * It consists of
+ *   (1) the kblas{S,D}<op>_batch[_strided] entry points, which already have C linkage in
+ *       the reference (include/kblas_batch.h:948-1053, 1486-1566, 2190-2278, 2896-2990);
+ *   (2) C-linkage twins of the management / workspace calls that the reference only
+ *       offers with C++ linkage (include/kblas.h:54-108; kblas_batch.h:773,786,1380,1391,
+ *       2077,2089,2772,2785; src/Xhelper_funcs.ch:48-55; src/kblas_common.h:35-36).
+ *       Same names, same arguments; cudaStream_t / cublasHandle_t appear as void*.
+ *       The mangled C++ symbols are exported as well (include/kblas.h), so code
+ *       compiled against the reference's headers links unchanged;
+ *   (3) a few kblasx_* introspection calls (no reference counterpart) used by the parity
+ *       tests and the bench.
+ *
+ * Do not include this header together with kblas.h in one C++ translation unit: the two
+ * declare the same names with different linkage on purpose.
+ */
+#ifndef KBLAS_B200_FFI_H
+#define KBLAS_B200_FFI_H
+
+#ifdef __cplusplus
+#error "kblas_ffi.h is the plain-C FFI view; C++ code includes kblas.h"
+#endif
+
+#include <stddef.h>
+#include "kblas_batch.h"   /* (1): kblas{S,D}{trsm,potrf,potrs,posv}_batch[_strided], kblas_roundup */
+
+/* (2) management -- reference include/kblas.h:54-108, src/kblas_common.cu:35-202 */
+int         kblasCreate(kblasHandle_t *handle);
+int         kblasDestroy(kblasHandle_t *handle);
+void        kblasTimerTic(kblasHandle_t handle);
+void        kblasTimerRecordEnd(kblasHandle_t handle);
+double      kblasTimerToc(kblasHandle_t handle);
+int         kblasCreateStreams(kblasHandle_t handle, int nStreams);
+void       *kblasGetStream(kblasHandle_t handle);                 /* cudaStream_t */
+void        kblasSetStream(kblasHandle_t handle, void *stream);   /* cudaStream_t */
+void       *kblasGetCublasHandle(kblasHandle_t handle);           /* cublasHandle_t */
+int         kblasEnableMagma(kblasHandle_t handle);
+const char *kblasGetErrorString(int error);
+int         kblasAllocateWorkspace(kblasHandle_t handle);
+int         kblasFreeWorkspace(kblasHandle_t handle);
+
+/* (2) workspace queries -- reference src/workspace_queries.cu:257-266,313-319,340-346,367-373 */
+void kblas_trsm_batch_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
+void kblas_trsm_batch_strided_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
+void kblas_potrf_batch_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_potrf_batch_strided_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_potrs_batch_wsquery(kblasHandle_t handle, int m, int n, int batchCount);
+void kblas_potrs_batch_strided_wsquery(kblasHandle_t handle, int m, int n, int batchCount);
+void kblas_posv_batch_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
+void kblas_posv_batch_strided_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
+
+/* (2) pointer-array / value helpers the reference's own test binaries call
+ *     (src/Xhelper_funcs.ch:48-55 -> S/D suffix replaces the C++ overload;
+ *      src/kblas_common.h:35-36).  output[i] = input + i*batch_offset. */
+int kblasSset_pointer_1(float **output_array, const float *input, int lda, long batch_offset,
+                        long batchCount, void *stream);
+int kblasDset_pointer_1(double **output_array, const double *input, int lda, long batch_offset,
+                        long batchCount, void *stream);
+int kblasSset_pointer_2(float **output_array1, const float *input1, int ld1, long batch_offset1,
+                        float **output_array2, const float *input2, int ld2, long batch_offset2,
+                        long batchCount, void *stream);
+int kblasDset_pointer_2(double **output_array1, const double *input1, int ld1, long batch_offset1,
+                        double **output_array2, const double *input2, int ld2, long batch_offset2,
+                        long batchCount, void *stream);
+int kblas_iset_value_1(int *output_array, int input, long batchCount, void *stream);
+
+/* (3) introspection: no reference counterpart */
+/** workspace bytes recorded in the handle: which = 0 requested, 1 allocated, 2 consumed;
+ *  out[4] = {h_data, h_ptrs, d_data, d_ptrs} (KBlasWorkspaceState, src/kblas_struct.h:43-91). */
+int         kblasx_workspace_state(kblasHandle_t handle, int which, size_t out[4]);
+/** pure host arithmetic of the *_wsquery cores, usable without a GPU or a handle.
+ *  op: 0 trsm, 1 potrf, 2 potrs, 3 posv.  out[4] as above. */
+int         kblasx_wsquery_bytes(int op, int strided, char side, int m, int n, int batchCount,
+                                 size_t out[4]);
+/** number of kernels this handle has launched since creation (the bench's gpu_launches). */
+long        kblasx_launch_count(kblasHandle_t handle);
+/** name of the kernel variant the most recent call on this handle dispatched to. */
+const char *kblasx_last_kernel(kblasHandle_t handle);
+/** library / build identification string ("kblas-b200 <ver> sm_100a ..."). */
+const char *kblasx_version(void);
+/** REG_SIZE / CLOSEST_REG_SIZE of the reference (src/kblas_common.cu:241-255). */
+int         kblasx_reg_size(int n);
+int         kblasx_closest_reg_size(int n);
+
+#endif /* KBLAS_B200_FFI_H */

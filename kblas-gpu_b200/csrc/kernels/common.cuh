@@ -1,0 +1,68 @@
+// kernels/common.cuh -- device helpers shared by the sm_100a batch kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace kblasx {
+
+template <typename T> struct Vec2T;
+template <> struct Vec2T<double> { typedef double2 type; };
+template <> struct Vec2T<float>  { typedef float2 type; };
+
+// elements per 32-byte DRAM/L2 sector
+template <typename T> struct SectorElems { static constexpr int value = 32 / (int)sizeof(T); };
+
+// ---- where matrix b of a batch lives --------------------------------------------------
+// strided: base + b*stride (reference "T* A, long strideA"); pointer array: base[b]
+// (reference "T** A": a DEVICE array of device pointers, dereferenced inside the kernel,
+//  Xpotrf_batch_kernels.cuh:92-97).  64-bit offsets throughout (8M x 1024 elements).
+template <typename T, bool STRIDED> struct BatchRef;
+template <typename T> struct BatchRef<T, true> {
+  T *base;
+  long stride;
+  __device__ __forceinline__ T *at(long b) const { return base + b * stride; }
+};
+template <typename T> struct BatchRef<T, false> {
+  T *const *base;
+  long stride;  // unused
+  __device__ __forceinline__ T *at(long b) const { return base[b]; }
+};
+
+// ---- streaming global access ----------------------------------------------------------
+// Every byte of a matrix is touched exactly once per kernel, so bypass L1 allocation.
+__device__ __forceinline__ double ldg_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float *p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(double *p, double v) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream(float *p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// ---- arithmetic -----------------------------------------------------------------------
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
+__device__ __forceinline__ float sqrt_t(float a) { return sqrtf(a); }
+__device__ __forceinline__ double rsqrt_t(double a) { return rsqrt(a); }
+__device__ __forceinline__ float rsqrt_t(float a) { return rsqrtf(a); }
+
+// width-G broadcast from lane `src` of each G-lane segment
+template <int G>
+__device__ __forceinline__ double shfl_seg(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src, G);
+}
+template <int G>
+__device__ __forceinline__ float shfl_seg(float v, int src) {
+  return __shfl_sync(0xffffffffu, v, src, G);
+}
+
+}  // namespace kblasx

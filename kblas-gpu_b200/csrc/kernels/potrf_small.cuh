@@ -1,0 +1,133 @@
+// kernels/potrf_small.cuh -- register-resident batched Cholesky for n <= 32 (sm_100a).
+//
+// Replaces the reference's 1-4 launches per call (K1-K4 potrf kernels + K5 trsm + K13 syrk,
+// Xpotrf_batch_kernels.cuh:37-488, driver recursion Xpotrf_batch_drivers.cuh:43-137) by ONE
+// launch in which every matrix is read once and written once.
+//
+// Mapping.  A group of G lanes owns one matrix, 32/G matrices per warp.  Lane l of the group
+// holds rows  G*s + l  (s = 0 .. NP/G-1, "slot") of the lower triangle: slot s keeps columns
+// 0 .. G*(s+1)-1, so the per-lane register footprint is G*S(S+1)/2 values (80 for n=32, G=8)
+// and the cyclic-by-slot row layout lets slot s drop out of the trailing update as soon as the
+// factorisation has passed its rows -- 230 FMA warp-instructions per n=32 matrix instead of
+// the 496 of a row-per-lane layout.
+//
+// Right-looking column step j (same recurrence as Xpotrf_batch_kernels.cuh:50-69):
+//   d = A[j][j] (width-G shuffle), r = 1/sqrt(d), column j *= r, publish column j through a
+//   double-buffered shared-memory line, every lane reads L[k][j] (k > j) back as broadcast
+//   128-bit loads and applies  A[i][k] -= L[i][j] * L[k][j]  to the rows it owns.
+// Shared memory replaces the reference's per-element __shfl broadcast (2 SHFL per fp64 value,
+// include/kblas_operators.h:88-97): 1 LDS.128 delivers two values to four matrices at once.
+//
+// Memory.  Column-major matrix b at A.at(b); a lane's G-row segment of one column is
+// contiguous (64 B for fp64, G=8), so every LDG/STG of a warp covers whole 32-byte sectors.
+// Sectors that lie entirely in the strict upper triangle are never loaded, and only
+// elements with row >= col are stored: the strict upper triangle is bit-preserved, as in
+// the reference (stores guarded by tx >= i, Xpotrf_batch_kernels.cuh:73-77).
+// n < NP is handled by padding with the identity in registers.
+#pragma once
+
+#include "common.cuh"
+
+namespace kblasx {
+
+template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
+                 const int info_mode) {
+  constexpr int S = NP / G;     // row slots per lane
+  constexpr int MPW = 32 / G;   // matrices per warp
+  constexpr int SE = SectorElems<T>::value;
+  constexpr int PAIR = MPW * 2;                 // elements per row pair in the broadcast line
+  constexpr int BUF_STRIDE = (NP / 2) * PAIR;   // elements per buffer
+  typedef typename Vec2T<T>::type V2;
+  static_assert(NP % G == 0 && G % 2 == 0 && 32 % G == 0, "bad tiling");
+
+  // broadcast line: [warp][buffer][row pair][matrix in warp][2]
+  __shared__ __align__(16) T bc[WARPS * 2 * BUF_STRIDE];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int l = lane % G;
+  const int g = lane / G;
+  const long mat = ((long)blockIdx.x * WARPS + warp) * MPW + g;
+  const bool active = mat < (long)batchCount;
+  T *__restrict__ A = active ? Aref.at(mat) : nullptr;
+
+#define KX_IDX(s_, c_) (G * (((s_) * ((s_) + 1)) / 2) + (c_))
+  T a[G * (S * (S + 1)) / 2];
+
+  // ---- load the lower triangle (whole sectors only) ---------------------------------------
+#pragma unroll
+  for (int col = 0; col < NP; ++col) {
+    const T *pc = A + l + (long)col * lda;
+#pragma unroll
+    for (int s = col / G; s < S; ++s) {
+      const int row = G * s + l;
+      const bool inside = (row < n) && (col < n);
+      const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
+      T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
+      if (active && inside && need) v = ldg_stream(pc + G * s);
+      a[KX_IDX(s, col)] = v;
+    }
+  }
+
+  int bad = 0;
+  T *const wbase = bc + warp * (2 * BUF_STRIDE) + g * 2;
+
+  // ---- right-looking factorisation ---------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int t = j / G, c = j % G;
+    const T d = shfl_seg<G>(a[KX_IDX(t, j)], c);
+    if (info_mode) {
+      if (bad == 0 && j < n && !(d > T(0))) bad = j + 1;
+    }
+    const T r = T(1) / sqrt_t(d);
+#pragma unroll
+    for (int s = t; s < S; ++s) a[KX_IDX(s, j)] *= r;
+
+    if (j + 1 < NP) {
+      T *wb = wbase + (j & 1) * BUF_STRIDE;
+      // publish column j (rows of every slot that still reaches below the diagonal)
+#pragma unroll
+      for (int s = t; s < S; ++s) {
+        if (G * s + G - 1 > j) {
+          const int k = G * s + l;
+          wb[(k >> 1) * PAIR + (k & 1)] = a[KX_IDX(s, j)];
+        }
+      }
+      __syncwarp();
+      // trailing update: A[i][k] -= L[i][j] * L[k][j] for every owned row i >= k > j.
+      // Rows above the diagonal inside the diagonal slot pick up garbage that is never
+      // published, read or stored (same as the reference's unguarded register updates).
+#pragma unroll
+      for (int p = (j + 1) / 2; p < NP / 2; ++p) {
+        const V2 v2 = *reinterpret_cast<const V2 *>(wb + p * PAIR);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = 2 * p + h;
+          if (k > j) {
+            const T v = h ? v2.y : v2.x;
+#pragma unroll
+            for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- store the lower triangle ------------------------------------------------------------
+#pragma unroll
+  for (int col = 0; col < NP; ++col) {
+    T *pc = A + l + (long)col * lda;
+#pragma unroll
+    for (int s = col / G; s < S; ++s) {
+      const int row = G * s + l;
+      if (active && row >= col && row < n) stg_stream(pc + G * s, a[KX_IDX(s, col)]);
+    }
+  }
+  if (info_mode && active && l == 0) info[mat] = bad;
+#undef KX_IDX
+}
+
+}  // namespace kblasx

@@ -1,0 +1,108 @@
+// potrf_batch.cu -- kblas_potrf_batch: entry points + dispatch.
+//
+// Counterpart of reference src/batch_triangular/Xpotrf_batch.cu:44-160 (entry points,
+// workspace check) and Xpotrf_batch_drivers.cuh:30-137 (driver).  The reference's driver
+// recursion (n/2 split -> potrf, trsm, syrk, potrf launches) is gone: one kernel per call.
+#include "kblas.h"
+#include "kblas_common.h"
+#include "kernels/potrf_small.cuh"
+#include "potrf_batch.h"
+
+namespace kblasx {
+
+template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED>
+static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
+                            int *info) {
+  constexpr int MPW = 32 / G;
+  const long per_cta = (long)WARPS * MPW;
+  const long grid = (batchCount + per_cta - 1) / per_cta;
+  potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+#define KX_STR2(x) #x
+#define KX_STR(x) KX_STR2(x)
+#define KX_LAUNCH_REG(NP, G, W, MB) \
+  launch_potrf_reg<T, NP, G, W, MB, STRIDED>(h, "potrf_reg<NP=" KX_STR(NP) ",G=" KX_STR(G) ",W=" KX_STR(W) ">", n, A, lda, batchCount, info)
+
+// n <= 32: register-resident kernel, padded size NP = roundup(n, 8)
+template <typename T, bool STRIDED>
+static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
+  const int v = h->variant_override;
+  if (n <= 8) return KX_LAUNCH_REG(8, 8, 4, 4);
+  if (n <= 16) return KX_LAUNCH_REG(16, 8, 4, 4);
+  if (n <= 24) return KX_LAUNCH_REG(24, 8, 4, 3);
+  switch (v) {
+    case 1: return KX_LAUNCH_REG(32, 16, 4, 3);
+    case 2: return KX_LAUNCH_REG(32, 8, 5, 2);
+    default: return KX_LAUNCH_REG(32, 8, 4, 2);
+  }
+}
+
+// Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)
+template <typename T, bool STRIDED>
+int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
+  if (uplo == KBLAS_Upper) {
+    printf("Upper POTRF_BATCH is not implemented yet\n");  // same line as the reference prints (:39)
+    return KBLAS_NotImplemented;
+  }
+  if (batchCount <= 0) {
+    // reference: grid.x == 0 -> launch error -> KBLAS_UnknownError (drivers.cuh:82-88)
+    check_error_ret(cudaErrorInvalidConfiguration, KBLAS_UnknownError);
+  }
+  if (n <= 0) return KBLAS_Success;  // reference launches a kernel that does nothing
+  if (n <= 32) return potrf_small_dispatch<T, STRIDED>(h, n, A, lda, batchCount, info);
+  return KBLAS_NotSupported;
+}
+
+template int potrf_batch_core<float, true>(KBlasHandle *, char, int, BatchRef<float, true>, int, int, int *);
+template int potrf_batch_core<float, false>(KBlasHandle *, char, int, BatchRef<float, false>, int, int, int *);
+template int potrf_batch_core<double, true>(KBlasHandle *, char, int, BatchRef<double, true>, int, int, int *);
+template int potrf_batch_core<double, false>(KBlasHandle *, char, int, BatchRef<double, false>, int, int, int *);
+
+// workspace check of Xpotrf_batch_offset (Xpotrf_batch.cu:50-56, 113-119)
+static int potrf_ws_check(KBlasHandle *h, bool strided, int n, int batchCount) {
+  KBlasWorkspaceState need;
+  potrf_batch_wsquery_core(strided, n, batchCount, &need);
+  return need.isSufficient(&h->work_space.allocated_ws_state) ? KBLAS_Success : KBLAS_InsufficientWorkspace;
+}
+
+template <typename T>
+int potrf_batch_strided(KBlasHandle *h, char uplo, int n, T *A, int lda, long strideA, int batchCount, int *info) {
+  if (potrf_ws_check(h, true, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
+  BatchRef<T, true> ref = {A, strideA};
+  return potrf_batch_core<T, true>(h, uplo, n, ref, lda, batchCount, info);
+}
+
+template <typename T>
+int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batchCount, int *info) {
+  if (potrf_ws_check(h, false, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
+  BatchRef<T, false> ref = {A, 0};
+  return potrf_batch_core<T, false>(h, uplo, n, ref, lda, batchCount, info);
+}
+
+}  // namespace kblasx
+
+// ---- public API: C++ overloads (reference Xpotrf_batch.cu:67-80,130-143) and C names (:86-98,149-160)
+#define KX_POTRF_API(P, T)                                                                                    \
+  int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount,         \
+                        int *info_array) {                                                                    \
+    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, lda, batchCount, info_array);                      \
+  }                                                                                                           \
+  int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA,            \
+                        int batchCount, int *info_array) {                                                    \
+    return kblasx::potrf_batch_strided<T>(handle, uplo, n, A, lda, strideA, batchCount, info_array);          \
+  }                                                                                                           \
+  extern "C" int kblas##P##potrf_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda,          \
+                                       int batchCount, int *info_array) {                                     \
+    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, lda, batchCount, info_array);                      \
+  }                                                                                                           \
+  extern "C" int kblas##P##potrf_batch_strided(kblasHandle_t handle, char uplo, const int n, T *A, int lda,   \
+                                               long strideA, int batchCount, int *info_array) {               \
+    return kblasx::potrf_batch_strided<T>(handle, uplo, n, A, lda, strideA, batchCount, info_array);          \
+  }
+KX_POTRF_API(S, float)
+KX_POTRF_API(D, double)

@@ -1,0 +1,13 @@
+// potrf_batch.h -- internal interface of the potrf dispatch (used by posv).
+#pragma once
+#include "kblas_struct.h"
+#include "kernels/common.cuh"
+
+namespace kblasx {
+template <typename T, bool STRIDED>
+int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info);
+template <typename T>
+int potrf_batch_strided(KBlasHandle *h, char uplo, int n, T *A, int lda, long strideA, int batchCount, int *info);
+template <typename T>
+int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batchCount, int *info);
+}  // namespace kblasx

@@ -1,0 +1,146 @@
+// trsm_batch.cu -- kblas_trsm_batch (+ the tri-solve dispatch shared with potrs/posv).
+//
+// Counterpart of reference src/batch_triangular/Xtrsm_batch.cu:42-257 (entry points,
+// workspace check) and Xtrsm_batch_drivers.cuh:54-272 (driver: kernel table + recursion
+// through cuBLAS batched GEMM).  Here: one launch per call.
+#include "kblas.h"
+#include "kblas_common.h"
+#include "kernels/trsm_small.cuh"
+#include "tri_batch.h"
+
+namespace kblasx {
+
+template <typename T, int NP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                            int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4;
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  const size_t smem = (size_t)WARPS * TriSmem<NP, LEFT>::per_warp * sizeof(T);
+  auto kern = tri_solve_small_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    KBLAS_CUDA_Error);
+    attr_set = true;
+  }
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+template <typename T, bool LEFT, int OP, bool STRIDED>
+static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                        BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 24) return launch_tri_small<T, 24, LEFT, OP, STRIDED>(h, "tri_small<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  return launch_tri_small<T, 32, LEFT, OP, STRIDED>(h, "tri_small<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+}
+
+// Solve with the k x k lower factor in A; `left` selects which side of B it acts on and `op`
+// forward / backward / both (see kernels/trsm_small.cuh).
+template <typename T, bool STRIDED>
+int tri_solve_core(KBlasHandle *h, bool left, int op, int m, int n, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                   BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  const int k = left ? m : n, vec = left ? n : m;
+  if (batchCount <= 0) {
+    check_error_ret(cudaErrorInvalidConfiguration, KBLAS_UnknownError);  // reference: empty grid
+  }
+  if (k > 32) return KBLAS_NotSupported;
+  if (vec <= 0) return KBLAS_Success;
+#define KX_TRI(L_, O_) tri_small_np<T, L_, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount)
+  if (left) {
+    if (op == TRI_FORWARD) return KX_TRI(true, TRI_FORWARD);
+    if (op == TRI_BACKWARD) return KX_TRI(true, TRI_BACKWARD);
+    return KX_TRI(true, TRI_BOTH);
+  }
+  if (op == TRI_FORWARD) return KX_TRI(false, TRI_FORWARD);
+  if (op == TRI_BACKWARD) return KX_TRI(false, TRI_BACKWARD);
+  return KX_TRI(false, TRI_BOTH);
+#undef KX_TRI
+}
+
+#define KX_INST(T, S)                                                                                      \
+  template int tri_solve_core<T, S>(KBlasHandle *, bool, int, int, int, T, BatchRef<const T, S>, int,      \
+                                    BatchRef<T, S>, int, int);
+KX_INST(float, true)
+KX_INST(float, false)
+KX_INST(double, true)
+KX_INST(double, false)
+#undef KX_INST
+
+// Xtrsm_batch_core of the reference (Xtrsm_batch_drivers.cuh:54-272)
+template <typename T, bool STRIDED>
+static int trsm_batch_core(KBlasHandle *h, char side, char uplo, char trans, char diag, int m, int n, T alpha,
+                           BatchRef<const T, STRIDED> A, int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  if (uplo == KBLAS_Upper || diag == KBLAS_Unit) {
+    printf("(Upper | Unit) TRSM_BATCH is not implemented yet\n");  // reference drivers.cuh:65
+    return KBLAS_NotImplemented;
+  }
+  const bool left = (side == KBLAS_Left);
+  if (!left && side != KBLAS_Right) return KBLAS_NotImplemented;
+  // the reference falls through to "should not reach this" when the triangular dimension is 0
+  if ((left ? m : n) <= 0) return KBLAS_NotImplemented;  // drivers.cuh:267-270
+  const bool notrans = (trans == KBLAS_NoTrans);
+  // forward: (R, T) and (L, N); backward: (R, N) and (L, T)
+  const int op = (left == notrans) ? TRI_FORWARD : TRI_BACKWARD;
+  return tri_solve_core<T, STRIDED>(h, left, op, m, n, alpha, A, lda, B, ldb, batchCount);
+}
+
+static int trsm_ws_check(KBlasHandle *h, bool strided, char side, int m, int n, int batchCount) {
+  KBlasWorkspaceState need;
+  trsm_batch_wsquery_core(strided, batchCount, side, m, n, &need);  // reference Xtrsm_batch.cu:196-203
+  return need.isSufficient(&h->work_space.allocated_ws_state) ? KBLAS_Success : KBLAS_InsufficientWorkspace;
+}
+
+template <typename T>
+int trsm_batch_strided(KBlasHandle *h, char side, char uplo, char trans, char diag, int m, int n, T alpha,
+                       const T *A, int lda, long strideA, T *B, int ldb, long strideB, int batchCount) {
+  if (trsm_ws_check(h, true, side, m, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
+  BatchRef<const T, true> a = {A, strideA};
+  BatchRef<T, true> b = {B, strideB};
+  return trsm_batch_core<T, true>(h, side, uplo, trans, diag, m, n, alpha, a, lda, b, ldb, batchCount);
+}
+
+template <typename T>
+int trsm_batch_ptrs(KBlasHandle *h, char side, char uplo, char trans, char diag, int m, int n, T alpha, const T **A,
+                    int lda, T **B, int ldb, int batchCount) {
+  if (trsm_ws_check(h, false, side, m, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
+  BatchRef<const T, false> a = {A, 0};
+  BatchRef<T, false> b = {B, 0};
+  return trsm_batch_core<T, false>(h, side, uplo, trans, diag, m, n, alpha, a, lda, b, ldb, batchCount);
+}
+
+}  // namespace kblasx
+
+// ---- public API (reference Xtrsm_batch.cu:60-112 pointer array, 218-257 strided)
+#define KX_TRSM_API(P, T)                                                                                      \
+  int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, const int m,         \
+                       const int n, const T alpha, const T **A, int lda, T **B, int ldb, int batchCount) {     \
+    return kblasx::trsm_batch_ptrs<T>(handle, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb,            \
+                                      batchCount);                                                             \
+  }                                                                                                            \
+  int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, const int m,         \
+                       const int n, const T alpha, const T *A, int lda, long strideA, T *B, int ldb,           \
+                       long strideB, int batchCount) {                                                         \
+    return kblasx::trsm_batch_strided<T>(handle, side, uplo, trans, diag, m, n, alpha, A, lda, strideA, B,     \
+                                         ldb, strideB, batchCount);                                            \
+  }                                                                                                            \
+  extern "C" int kblas##P##trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,       \
+                                      const int m, const int n, const T alpha, const T **A, int lda, T **B,    \
+                                      int ldb, int batchCount) {                                               \
+    return kblasx::trsm_batch_ptrs<T>(handle, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb,            \
+                                      batchCount);                                                             \
+  }                                                                                                            \
+  extern "C" int kblas##P##trsm_batch_strided(kblasHandle_t handle, char side, char uplo, char trans,          \
+                                              char diag, const int m, const int n, const T alpha, const T *A,  \
+                                              int lda, long strideA, T *B, int ldb, long strideB,              \
+                                              int batchCount) {                                                \
+    return kblasx::trsm_batch_strided<T>(handle, side, uplo, trans, diag, m, n, alpha, A, lda, strideA, B,     \
+                                         ldb, strideB, batchCount);                                            \
+  }
+KX_TRSM_API(S, float)
+KX_TRSM_API(D, double)
