@@ -1,0 +1,509 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched very-small-matrix Cholesky path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU, N > 1)
+
+Metric (BASELINE.json): strided dpotrf_batch, n = 32, fp64, matrices/s (and GFLOP/s) as a fraction
+of the HBM roofline.  One "step" = one kblasDpotrf_batch_strided call over the whole batch of
+synthetic random SPD matrices (uniform [0,1) + n*I, the reference harness's distribution,
+testing/testing_helper.cu:353-402).
+  * N = 1: batch = 2^20 (configs[1] at n = 32, the configuration the metric is quoted on).
+  * N > 1: batch = 2^23 split by contiguous slab over the ranks (configs[4], "strong" scaling:
+    total work fixed); no data-path collective exists -- torch.distributed only provides the
+    barrier and the max-over-ranks reduction of the device time.
+Prints ONE JSON line on rank 0.  `value` is device-resident throughput (inputs in HBM, CUDA-event
+timed on the launching stream, max over ranks); `e2e` is the same call with HOST (pinned) buffers,
+host<->device copies inside the timed region.  `roofline` uses the algorithmic bytes of SURVEY.md
+§8(d) (lower triangle read + written = n(n+1)*8 B = 8448 B per matrix) and the measured HBM peak of
+MEASURED_PEAKS.json.  `cpu_baseline` is the reference harness's LAPACK dpotrf loop
+(test_Xpotrf_batch.cpp:308-321) on the host cores -- a reported baseline, not the target.
+
+--impl reference runs the UNMODIFIED reference GPU library (oracle/_ref/libkblas_ref.so, built from
+/root/reference by oracle/build_ref.sh) through the same harness; if that library cannot be loaded
+it falls back to the reference harness's CPU LAPACK loop (also available as --impl reference-cpu).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_MAT = 32
+ELEM = 8  # fp64
+ALGO_BYTES = N_MAT * (N_MAT + 1) * ELEM              # 8448: lower read + lower written
+FLOPS = N_MAT ** 3 / 3 + N_MAT ** 2 / 2 + N_MAT / 6   # 11440 (testing/flops.h:86-93)
+FALLBACK_HBM_GBS = 6650.0                             # B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                mhz, mmx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx.append(mmx)
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(mhz)
+                try:
+                    pw.append(float(f[3]))
+                except ValueError:
+                    pass
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use everything we saw
+            sm = [float(l.split(",")[1]) for _, l in self.rows if len(l.split(",")) >= 9] or [0.0]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_spd(torch, batch, n, dtype, seed):
+    """(batch, n, n) device tensor, memory = column-major matrices with lda = n, stride = n*n.
+    Built in slices to bound the transient memory."""
+    out = torch.empty((batch, n, n), device="cuda", dtype=dtype)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    step = 1 << 18
+    for lo in range(0, batch, step):
+        hi = min(batch, lo + step)
+        a = torch.rand((hi - lo, n, n), generator=g, device="cuda", dtype=dtype)
+        a = torch.tril(a) + torch.tril(a, -1).transpose(1, 2)
+        a.diagonal(dim1=1, dim2=2).add_(n)
+        out[lo:hi] = a
+    return out
+
+
+class OursImpl:
+    name = "ours"
+
+    def __init__(self):
+        self.kb = importlib.import_module("kblas-gpu_b200")   # raises if the CUDA library is missing
+        self.h = self.kb.Handle()
+
+    def prepare(self, n, batch):
+        self.h.potrf_batch_strided_wsquery(n, batch)
+        assert self.h.allocate_workspace() == 1
+
+    def set_stream(self, s):
+        self.h.set_stream(s)
+
+    def potrf(self, A, n, batch):
+        rc = self.h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
+        if rc != 1:
+            raise RuntimeError(self.kb.error_string(rc))
+
+    def potrf_ptr(self, ptr, n, batch):
+        rc = self.h.potrf_batch_strided("L", n, ptr, n, n * n, batch, None, prec="D")
+        if rc != 1:
+            raise RuntimeError(self.kb.error_string(rc))
+
+    def launches_per_step(self, n):
+        before = self.h.launch_count
+        return before
+
+    def kernel_name(self):
+        return self.h.last_kernel
+
+
+class RefGpuImpl:
+    """the unmodified reference library, through its own public API"""
+    name = "reference"
+
+    def __init__(self):
+        from tests._util import RefLib
+
+        self.ref = RefLib()
+        r = self.ref
+        self._potrf = r.fn("kblasDpotrf_batch_strided", [r.H, r.c, r.i, r.P, r.i, r.l, r.i, r.P])
+        self._set_stream = getattr(r.lib, "_Z14kblasSetStreamP11KBlasHandleP11CUstream_st")
+        self._set_stream.argtypes = [r.H, C.c_void_p]
+        self._set_stream.restype = None
+
+    def prepare(self, n, batch):
+        self.ref.wsquery("kblas_potrf_batch_strided_wsquery", "ii", n, batch)
+        assert self.ref.allocate() == 1
+
+    def set_stream(self, s):
+        self._set_stream(self.ref.h, getattr(s, "cuda_stream", s))
+
+    def potrf(self, A, n, batch):
+        rc = self._potrf(self.ref.h, b"L", n, A.data_ptr(), n, n * n, batch, None)
+        if rc != 1:
+            raise RuntimeError(f"reference potrf rc={rc}")
+
+    def potrf_ptr(self, ptr, n, batch):
+        rc = self._potrf(self.ref.h, b"L", n, ptr, n, n * n, batch, None)
+        if rc != 1:
+            raise RuntimeError(f"reference potrf rc={rc}")
+
+    def kernel_name(self):
+        return "kernel_potrf_U_registers_fixN_blocked_2 x2 + trsm + syrk (4 launches, n=32)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_lapack_loop(n, sample, threads_list, runs=3):
+    """reference harness CPU check loop (test_Xpotrf_batch.cpp:308-321) on a bounded sample"""
+    import numpy as np
+
+    from tests import _util as U
+
+    if not os.path.exists(U.LAPACK_LOOP_SO):
+        subprocess.check_call(["make", "-C", U.ORACLE_DIR, "liblapack_loop.so"], stdout=subprocess.DEVNULL)
+    loop = C.CDLL(U.LAPACK_LOOP_SO)
+    ob = U.lapack_lib()
+    ob.scipy_openblas_set_num_threads(1)
+    potrf = C.cast(ob.scipy_dpotrf_, C.c_void_p)
+    loop.lapack_potrf_loop.restype = C.c_double
+    loop.lapack_potrf_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int,
+                                       C.POINTER(C.c_long)]
+    pristine = U.rand_spd_batch(sample, n, dtype=np.float64, seed=1)
+    out = {}
+    for th in threads_list:
+        best = None
+        for _ in range(runs):
+            A = pristine.copy()
+            bad = C.c_long(0)
+            sec = loop.lapack_potrf_loop(potrf, 8, n, A.ctypes.data_as(C.c_void_p), n, n * n, sample, th, C.byref(bad))
+            assert bad.value == 0
+            best = sec if best is None else min(best, sec)
+        out[th] = sample / best
+    return out
+
+
+def cpu_baseline_obj(n, sample=1 << 18):
+    cores = os.cpu_count() or 1
+    r = cpu_lapack_loop(n, sample, sorted({1, cores}))
+    return {"value": r[cores], "unit": "matrices/s", "cores": cores, "kind": "port",
+            "value_1core": r[1],
+            "sample": f"{sample} random SPD {n}x{n} fp64 matrices (1/{(1 << 20) // sample} of the N=1 workload), best of 3; "
+                      f"serial LAPACK dpotrf loop of the reference harness (test_Xpotrf_batch.cpp:308-321) restated in "
+                      f"oracle/lapack_loop.c over scipy's OpenBLAS, OpenMP over matrices for cores>1"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--batch", type=int, default=0, help="override the total batch (default 2^20 at N=1, 2^23 at N>1)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = N_MAT
+
+    # ---- CPU-only reference arm ---------------------------------------------------------------------
+    if args.impl == "reference-cpu":
+        if rank != 0:
+            return
+        sample = 1 << 18
+        cores = os.cpu_count() or 1
+        vals = []
+        t0 = time.time()
+        for _ in range(W):
+            cpu_lapack_loop(n, sample, [cores], runs=1)
+        for _ in range(K):
+            vals.append(cpu_lapack_loop(n, sample, [cores], runs=1)[cores])
+        v = len(vals) * sample / sum(sample / x for x in vals)
+        line = {"impl": "reference", "metric": "dpotrf_batch_strided n=32 fp64 throughput", "value": v, "unit": "matrices/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * sample / v, "higher_is_better": True,
+                "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"reference harness CPU LAPACK dpotrf loop, n=32 fp64, sample {sample} matrices/step"},
+                "cpu_baseline": {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
+                                 "sample": f"{sample} matrices per step"},
+                "e2e": {"value": v, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.time() - t0}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    total_batch = args.batch or ((1 << 20) if world == 1 else (1 << 23))
+    slab = importlib.import_module("kblas-gpu_b200.slab")
+    b0, b1 = slab.slab_range(total_batch, world, rank)
+    batch = b1 - b0
+
+    impl = None
+    if args.impl == "reference":
+        try:
+            impl = RefGpuImpl()
+        except Exception as e:  # library missing / not loadable on this box
+            log(f"[bench] reference GPU library unavailable ({e}); falling back to the CPU LAPACK loop")
+            if dist:
+                dist.destroy_process_group()
+            if rank == 0:
+                os.execv(sys.executable, [sys.executable, __file__, "--impl", "reference-cpu", "--gpus", str(args.gpus),
+                                          "--steps", str(K), "--warmup", str(W)])
+            return
+    else:
+        impl = OursImpl()
+    impl.prepare(n, batch)
+
+    stream = torch.cuda.Stream()
+    impl.set_stream(stream)
+
+    # ---- device-resident inputs: one pristine batch + as many working copies as fit -----------------
+    bytes_batch = batch * n * n * ELEM
+    free, _ = torch.cuda.mem_get_info()
+    pristine = make_spd(torch, batch, n, torch.float64, seed=1 + rank)
+    nbuf = int(max(1, min(K, (0.55 * free - bytes_batch) // bytes_batch)))
+    bufs = [torch.empty_like(pristine) for _ in range(nbuf)]
+    log(f"[bench] rank {rank}/{world}: batch {batch} ({bytes_batch / 2**30:.2f} GiB), {nbuf} working buffers")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    for i in range(W):
+        bufs[i % nbuf].copy_(pristine)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            impl.potrf(bufs[i % nbuf], n, batch)
+        stream.synchronize()
+
+    launches0 = impl.h.launch_count if args.impl == "ours" else 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.2)
+    total_ms, per_step_ms, done = 0.0, [], 0
+    wall0 = time.time()
+    while done < K:
+        nb = min(nbuf, K - done)
+        for i in range(nb):
+            bufs[i].copy_(pristine)           # untimed restore (potrf is in place)
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nb + 1)]
+        with torch.cuda.stream(stream):
+            evs[0].record(stream)
+            for i in range(nb):
+                impl.potrf(bufs[i], n, batch)
+                evs[i + 1].record(stream)
+        barrier()
+        total_ms += evs[0].elapsed_time(evs[nb])
+        per_step_ms += [evs[i].elapsed_time(evs[i + 1]) for i in range(nb)]
+        done += nb
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1)
+    launches = (impl.h.launch_count - launches0) if args.impl == "ours" else 4 * K
+
+    # quick sanity on the last result (outside the timed region): residual of a slice
+    L = torch.triu(bufs[0][:2048]).transpose(1, 2)
+    Am = pristine[:2048].transpose(1, 2)
+    res = ((Am - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
+    assert res <= 10 * n * 2.220446049250313e-16, f"residual {res}"
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / K
+    value = total_batch / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's own launch durations) -------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    kernel_ms = statistics.mean(per_step_ms)
+    achieved = batch * ALGO_BYTES / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.impl == "ours":
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch_n32_batch1M")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_matrix": ALGO_BYTES,
+                "matrices_per_launch": batch, "kernel": impl.kernel_name(), "kernel_ms_mean": kernel_ms,
+                "kernel_ms_min": min(per_step_ms)}
+
+    # ---- e2e: the same call with host (pinned) buffers, copies inside the timed region ---------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, dist, impl, n, batch, total_batch, pristine, rank)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline_obj(n)
+        except Exception as e:
+            cpu = {"value": None, "unit": "matrices/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": "dpotrf_batch_strided n=32 fp64 throughput",
+            "value": value, "unit": "matrices/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"strided dpotrf_batch n=32 lda=32 batch={total_batch} fp64 "
+                                   f"({'BASELINE configs[1] at n=32' if world == 1 else 'BASELINE configs[4], contiguous slabs'})",
+                       "batch_total": total_batch, "batch_per_gpu": batch, "n": n, "uplo": "L",
+                       "l2_policy": f"inputs larger than L2: {bytes_batch / 2**30:.1f} GiB per step per GPU, a fresh buffer every step",
+                       "parallelism": f"batch slab x{world}, no collective"},
+            "gflops": value * FLOPS / 1e9,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["reference_kind"] = "unmodified KBLAS-GPU sources compiled for sm_100 (oracle/_ref/libkblas_ref.so)"
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dist, impl, n, batch, total_batch, pristine, rank, steps=3, warmup=1):
+    """host pinned in -> H2D -> potrf -> D2H -> host pinned out, chunked and pipelined over 3 streams"""
+    chunk = min(batch, 1 << 16)
+    nchunks = (batch + chunk - 1) // chunk
+    elems = n * n
+    # host window: the slab is streamed through pinned buffers of at most 2^20 matrices (8 GiB each
+    # way); for larger slabs the window is reused -- every byte of the slab still crosses PCIe.
+    window = min(batch, 1 << 20)
+    try:
+        h_in = torch.empty((window, n, n), dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty((window, n, n), dtype=torch.float64, pin_memory=True)
+    except RuntimeError as e:
+        return {"value": None, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": f"pinned allocation failed: {e}"}
+    h_in.copy_(pristine[:window])
+    torch.cuda.synchronize()
+    NB = 3
+    dbuf = [torch.empty((chunk, n, n), dtype=torch.float64, device="cuda") for _ in range(NB)]
+    s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    impl.set_stream(s_k)
+    ev_in = [torch.cuda.Event() for _ in range(NB)]
+    ev_k = [torch.cuda.Event() for _ in range(NB)]
+    ev_out = [torch.cuda.Event() for _ in range(NB)]
+
+    def one_step():
+        for c in range(nchunks):
+            lo = (c * chunk) % window
+            hi = min(window, lo + min(chunk, batch - c * chunk))
+            b = c % NB
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_out[b])                 # buffer free again
+                dbuf[b][: hi - lo].copy_(h_in[lo:hi], non_blocking=True)
+                ev_in[b].record(s_in)
+            with torch.cuda.stream(s_k):
+                s_k.wait_event(ev_in[b])
+                impl.potrf(dbuf[b], n, hi - lo)
+                ev_k[b].record(s_k)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k[b])
+                h_out[lo:hi].copy_(dbuf[b][: hi - lo], non_blocking=True)
+                ev_out[b].record(s_out)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        one_step()
+    sync_all()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream())
+    for _ in range(steps):
+        one_step()
+    for s in (s_in, s_k, s_out):
+        torch.cuda.current_stream().wait_stream(s)
+    e1.record(torch.cuda.current_stream())
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    wall = time.perf_counter() - t0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # correctness of what came back to the host
+    L = torch.triu(h_out[:1024].cuda()).transpose(1, 2)
+    Am = h_in[:1024].cuda().transpose(1, 2)
+    res = ((Am - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
+    ok = res <= 10 * n * 2.220446049250313e-16
+    nbytes = batch * elems * ELEM
+    return {"value": total_batch * steps / (ms * 1e-3), "unit": "matrices/s", "h2d_bytes_per_step": nbytes,
+            "d2h_bytes_per_step": nbytes, "steps": steps, "ms_per_step": ms / steps, "wall_s": wall,
+            "pipeline": f"{nchunks} chunks of {chunk} matrices, 3 streams (H2D / potrf / D2H), pinned host buffers",
+            "residual_ok": bool(ok)}
+
+
+if __name__ == "__main__":
+    main()

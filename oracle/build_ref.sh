@@ -56,5 +56,5 @@ for f in kblas_common workspace_queries; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-nvcc -shared -o "$O/libkblas_ref.so" "$O"/obj/*.o -lcublas -Xlinker --no-undefined
+nvcc -shared -o "$O/libkblas_ref.so" "$O"/obj/*.o -lcublas -Xlinker --no-undefined -Xlinker -rpath=/usr/local/cuda/lib64
 ls -la "$O/libkblas_ref.so"

@@ -1,0 +1,473 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle, the committed
+golden vectors of the reference GPU library, and (when oracle/_ref was built) the reference library
+run live on the same device buffers.
+
+Tolerances are BASELINE.json's: per-matrix ||A - L L^T||_F / ||A||_F <= 10 n eps; element-wise
+deviation from the reference factor <= 100 n eps ||A||; info flags bit-identical (the reference
+never writes them); return codes identical.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+DT = {"D": np.float64, "S": np.float32}
+SENT = 77
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    kb = U.kblas()
+    h = kb.Handle()
+    yield kb, h, torch
+    h.destroy()
+
+
+def _dev(torch, a):
+    return torch.from_numpy(a).cuda()
+
+
+def _check_potrf(A0, A1, n, dt, Lref=None):
+    eps = U.EPS[dt]
+    assert U.potrf_residual(A0, A1, n) <= 10 * n * eps
+    M0, M1 = U.as_mats(A0, n, n), U.as_mats(A1, n, n)
+    assert np.array_equal(np.triu(M0, 1), np.triu(M1, 1)), "strict upper triangle must be bit-preserved"
+    assert np.array_equal(A0[:, :, n:], A1[:, :, n:]), "rows beyond n (lda padding) must be untouched"
+    assert np.array_equal(A0[:, n:, :], A1[:, n:, :]), "columns beyond n (stride padding) must be untouched"
+    if Lref is not None:
+        normA = np.abs(M0).max()
+        assert np.abs(np.tril(M1) - np.tril(U.as_mats(Lref, n, n))).max() <= 100 * n * eps * normA
+
+
+# =============================================================================================
+# potrf
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 9, 13, 16, 17, 23, 24, 25, 31, 32])
+def test_potrf_strided_vs_oracle(env, p, n):
+    kb, h, torch = env
+    dt = DT[p]
+    for batch, pad, extra in ((37, 0, 0), (1, 3, 2), (1000, 1, 0)):
+        lda = n + pad
+        A0 = U.rand_spd_batch(batch, n, lda=lda, dtype=dt, seed=n + batch, extra_cols=extra)
+        dA = _dev(torch, A0)
+        info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+        h.potrf_batch_strided_wsquery(n, batch)
+        h.allocate_workspace()
+        rc = h.potrf_batch_strided("L", n, dA, lda, (n + extra) * lda, batch, info)
+        torch.cuda.synchronize()
+        assert rc == kb.KBLAS_Success
+        Lo = A0.copy()
+        U.oracle_potrf(Lo, n)
+        _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
+        assert (info.cpu().numpy() == SENT).all(), "info must not be written (reference parity)"
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [8, 16, 24, 32, 20])
+def test_potrf_pointer_array_shuffled(env, p, n):
+    kb, h, torch = env
+    dt = DT[p]
+    batch = 531
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=3 * n)
+    dA = _dev(torch, A0)
+    perm = np.random.default_rng(n).permutation(batch)
+    esz = A0.itemsize
+    ptrs = torch.from_numpy((dA.data_ptr() + perm.astype(np.int64) * n * n * esz)).cuda()
+    h.potrf_batch_wsquery(n, batch)
+    h.allocate_workspace()
+    rc = h.potrf_batch("L", n, ptrs, n, batch, None, prec=p)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    Lo = A0.copy()
+    U.oracle_potrf(Lo, n)
+    _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
+    # pointer array built by the library helper (Xset_pointer_1), contiguous order
+    dA2 = _dev(torch, A0)
+    ptr2 = torch.zeros(batch, dtype=torch.int64, device="cuda")
+    assert h.set_pointer_1(ptr2, dA2, n, n * n, batch) == kb.KBLAS_Success
+    assert h.potrf_batch("L", n, ptr2, n, batch, None, prec=p) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert np.array_equal(dA2.cpu().numpy(), dA.cpu().numpy())
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [33, 40, 64, 100, 128, 200, 256])
+def test_potrf_strided_large_n(env, p, n):
+    kb, h, torch = env
+    dt = DT[p]
+    batch = 9
+    A0 = U.rand_spd_batch(batch, n, lda=n + (n % 3), dtype=dt, seed=n)
+    dA = _dev(torch, A0)
+    h.potrf_batch_strided_wsquery(n, batch)
+    h.allocate_workspace()
+    rc = h.potrf_batch_strided("L", n, dA, A0.shape[2], n * A0.shape[2], batch, None)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    Lo = A0.copy()
+    U.oracle_potrf(Lo, n)
+    _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
+
+
+def test_potrf_return_codes(env):
+    kb, h, torch = env
+    n, batch = 16, 4
+    dA = _dev(torch, U.rand_spd_batch(batch, n))
+    before = dA.clone()
+    assert h.potrf_batch_strided("U", n, dA, n, n * n, batch, None) == kb.KBLAS_NotImplemented
+    assert h.potrf_batch_strided("L", n, dA, n, n * n, 0, None) == kb.KBLAS_UnknownError  # empty grid in the reference
+    assert h.potrf_batch_strided("L", 0, dA, n, n * n, batch, None) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert torch.equal(dA, before)
+    # workspace protocol: pointer-array potrf with n = 64 needs d_ptrs (reference Xpotrf_batch.cu:50-56)
+    h2 = kb.Handle()
+    ptrs = torch.zeros(batch, dtype=torch.int64, device="cuda")
+    assert h2.potrf_batch("L", 64, ptrs, 64, batch, None) == kb.KBLAS_InsufficientWorkspace
+    h2.potrf_batch_wsquery(64, batch)
+    assert h2.workspace_state("requested") == (0, 0, 0, batch * 24)
+    assert h2.allocate_workspace() == kb.KBLAS_Success
+    assert h2.workspace_state("allocated") == (0, 0, 0, batch * 24)
+    assert h2.workspace_state("requested") == (0, 0, 0, 0)
+    h2.destroy()
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+def test_potrf_non_spd_matches_reference_behaviour(env, p):
+    kb, h, torch = env
+    dt = DT[p]
+    n, batch = 32, 40
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=9)
+    A0[3, 5, 5] = -3.0
+    A0[17, 20, 20] = 0.0
+    dA = _dev(torch, A0)
+    info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    assert h.potrf_batch_strided("L", n, dA, n, n * n, batch, info) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    Lo = A0.copy()
+    U.oracle_potrf(Lo, n)
+    got = np.tril(U.as_mats(dA.cpu().numpy(), n, n))
+    assert np.array_equal(np.isfinite(got), np.isfinite(np.tril(U.as_mats(Lo, n, n))))
+    assert (info.cpu().numpy() == SENT).all()
+
+
+def test_potrf_lapack_info_mode_is_opt_in(env):
+    kb, _, torch = env
+    os.environ["KBLAS_B200_INFO_MODE"] = "lapack"
+    try:
+        h = kb.Handle()
+    finally:
+        del os.environ["KBLAS_B200_INFO_MODE"]
+    n, batch = 32, 20
+    A0 = U.rand_spd_batch(batch, n, seed=10)
+    A0[3, 5, 5] = -3.0
+    A0[17, 20, 20] = -1.0
+    dA = _dev(torch, A0)
+    info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    assert h.potrf_batch_strided("L", n, dA, n, n * n, batch, info) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    want = np.zeros(batch, dtype=np.int32)
+    want[3], want[17] = 6, 21
+    assert np.array_equal(info.cpu().numpy(), want)
+    h.destroy()
+
+
+# =============================================================================================
+# trsm / potrs / posv
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
+@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (32, 32), (13, 7), (7, 13), (32, 20), (20, 32), (1, 1), (24, 24), (32, 100), (100, 32)])
+def test_trsm_strided_vs_oracle(env, p, side, trans, m, n):
+    kb, h, torch = env
+    dt = DT[p]
+    k = m if side == "L" else n
+    if k > 32:
+        pytest.skip("covered by test_trsm_large_k")
+    batch, alpha = 67, 0.28
+    A = U.rand_spd_batch(batch, k, lda=k + 1, dtype=dt, seed=k)
+    B0 = U.rand_batch(batch, m, n, ld=m + 2, dtype=dt, seed=m * 100 + n)
+    dA, dB = _dev(torch, A), _dev(torch, B0)
+    h.trsm_batch_strided_wsquery(side, m, n, batch)
+    h.allocate_workspace()
+    rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, alpha, dA, k + 1, k * (k + 1), dB, m + 2, n * (m + 2), batch)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    Bo = B0.copy()
+    U.oracle_trsm(side, "L", trans, "N", m, n, alpha, A, Bo)
+    got = dB.cpu().numpy()
+    assert np.abs(got - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :m]).max())
+    assert np.array_equal(got[:, :, m:], B0[:, :, m:])
+    assert np.array_equal(dA.cpu().numpy(), A), "A is read-only"
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
+@pytest.mark.parametrize("k,other", [(33, 16), (64, 16), (100, 40), (128, 16), (256, 16)])
+def test_trsm_large_k(env, p, side, trans, k, other):
+    kb, h, torch = env
+    dt = DT[p]
+    m, n = (k, other) if side == "L" else (other, k)
+    batch, alpha = 5, 0.28
+    A = U.rand_spd_batch(batch, k, dtype=dt, seed=k)
+    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=m * 100 + n)
+    dA, dB = _dev(torch, A), _dev(torch, B0)
+    h.trsm_batch_strided_wsquery(side, m, n, batch)
+    h.allocate_workspace()
+    rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, alpha, dA, k, k * k, dB, m, n * m, batch)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    Bo = B0.copy()
+    U.oracle_trsm(side, "L", trans, "N", m, n, alpha, A, Bo)
+    assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
+
+
+def test_trsm_potrs_posv_return_codes(env):
+    kb, h, torch = env
+    dA, dB = _dev(torch, U.rand_spd_batch(2, 8)), _dev(torch, U.rand_batch(2, 8, 8))
+    a = (dA, 8, 64, dB, 8, 64, 2)
+    assert h.trsm_batch_strided("L", "U", "N", "N", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
+    assert h.trsm_batch_strided("L", "L", "N", "U", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
+    assert h.potrs_batch_strided("L", "L", 8, 8, *a) == kb.KBLAS_NotImplemented
+    assert h.potrs_batch_strided("R", "U", 8, 8, *a) == kb.KBLAS_NotImplemented
+    assert h.posv_batch_strided("L", "L", 8, 8, *a, None) == kb.KBLAS_NotImplemented
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (24, 24), (32, 32), (16, 32), (5, 13), (40, 32), (3, 1)])
+def test_potrs_and_posv_strided_vs_oracle(env, p, m, n):
+    kb, h, torch = env
+    dt = DT[p]
+    batch = 45
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n + 1)
+    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=n + 2)
+    Ao, Bo = A0.copy(), B0.copy()
+    U.oracle_posv("R", "L", m, n, Ao, Bo)
+    tol = 100 * n * U.EPS[dt] * max(1.0, np.abs(Bo).max())
+    # posv
+    dA, dB = _dev(torch, A0), _dev(torch, B0)
+    info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    h.posv_batch_strided_wsquery("R", m, n, batch)
+    h.allocate_workspace()
+    assert h.posv_batch_strided("R", "L", m, n, dA, n, n * n, dB, m, m * n, batch, info) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Ao)
+    assert np.abs(dB.cpu().numpy() - Bo).max() <= tol
+    assert (info.cpu().numpy() == SENT).all()
+    # potrs from the oracle's factor
+    dL, dB2 = _dev(torch, Ao), _dev(torch, B0)
+    assert h.potrs_batch_strided("R", "L", m, n, dL, n, n * n, dB2, m, m * n, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert np.abs(dB2.cpu().numpy() - Bo).max() <= tol
+    assert np.array_equal(dL.cpu().numpy(), Ao)
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_posv_pointer_array_large_n(env, p, n):
+    """BASELINE config 4: pointer-array posv, n = 64/128/256, 16 right-hand-side rows"""
+    kb, h, torch = env
+    dt = DT[p]
+    m, batch = 16, 12
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n + 5)
+    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=n + 6)
+    Ao, Bo = A0.copy(), B0.copy()
+    U.oracle_posv("R", "L", m, n, Ao, Bo)
+    dA, dB = _dev(torch, A0), _dev(torch, B0)
+    perm = np.random.default_rng(n).permutation(batch).astype(np.int64)
+    pa = torch.from_numpy(dA.data_ptr() + perm * n * n * A0.itemsize).cuda()
+    pb = torch.from_numpy(dB.data_ptr() + perm * m * n * A0.itemsize).cuda()
+    h.posv_batch_wsquery("R", m, n, batch)
+    h.allocate_workspace()
+    assert h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, None, prec=p) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Ao)
+    assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * n * U.EPS[dt] * max(1.0, np.abs(Bo).max())
+
+
+# =============================================================================================
+# golden vectors of the reference GPU library
+def _gold():
+    path = os.path.join(U.GOLDEN_DIR, "reference_gpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not generated yet")
+    z = np.load(path)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        cases.setdefault(name, {})[field] = z[key]
+    return cases
+
+
+def _num(name, tag):
+    for part in name.split("_"):
+        if part.startswith(tag) and part[len(tag):].isdigit():
+            return int(part[len(tag):])
+    raise KeyError(name)
+
+
+def test_golden_vectors_through_the_c_abi(env):
+    kb, h, torch = env
+    seen = 0
+    for name, c in _gold().items():
+        kind, p = name.split("_")[0], name.split("_")[1]
+        if "A_in" not in c and "L_in" not in c:
+            continue
+        dt = DT[p]
+        if kind == "potrf":
+            n = _num(name, "n")
+            lda = c["A_in"].shape[2]
+            batch = c["A_in"].shape[0]
+            dA = _dev(torch, c["A_in"])
+            info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+            h.potrf_batch_strided_wsquery(n, batch)
+            h.allocate_workspace()
+            rc = h.potrf_batch_strided("L", n, dA, lda, n * lda, batch, info)
+            torch.cuda.synchronize()
+            assert rc == int(c["rc"]), name
+            got = dA.cpu().numpy()
+            if "nonspd" in name:
+                assert np.array_equal(np.isfinite(np.tril(U.as_mats(got, n, n))), np.isfinite(np.tril(U.as_mats(c["A_out"], n, n)))), name
+            else:
+                _check_potrf(c["A_in"], got, n, dt, Lref=c["A_out"])
+            assert np.array_equal(info.cpu().numpy(), c["info"]), name
+        else:
+            m, n = _num(name, "m"), _num(name, "n")
+            batch = c["B_in"].shape[0]
+            dB = _dev(torch, c["B_in"])
+            if kind == "trsm":
+                side, trans = name.split("_")[2]
+                k = m if side == "L" else n
+                dA = _dev(torch, c["A_in"])
+                h.trsm_batch_strided_wsquery(side, m, n, batch)
+                h.allocate_workspace()
+                rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, float(c["alpha"]), dA, k, k * k, dB, m, m * n, batch)
+            elif kind == "potrs":
+                k = n
+                if n == 1:
+                    continue  # documented deviation: the reference refuses n == 1, we solve it
+                dA = _dev(torch, c["L_in"])
+                h.potrs_batch_strided_wsquery(m, n, batch)
+                h.allocate_workspace()
+                rc = h.potrs_batch_strided("R", "L", m, n, dA, n, n * n, dB, m, m * n, batch)
+            else:
+                k = n
+                dA = _dev(torch, c["A_in"])
+                h.posv_batch_strided_wsquery("R", m, n, batch)
+                h.allocate_workspace()
+                rc = h.posv_batch_strided("R", "L", m, n, dA, n, n * n, dB, m, m * n, batch, None)
+            torch.cuda.synchronize()
+            assert rc == int(c["rc"]) == 1, name
+            ref = c["B_out"]
+            assert np.abs(dB.cpu().numpy() - ref).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(ref).max()), name
+        seen += 1
+    assert seen >= 80
+
+
+# =============================================================================================
+# live A/B against the unmodified reference library on identical device buffers
+@pytest.mark.parametrize("p", ["D", "S"])
+def test_live_against_reference_library(env, p):
+    if not U.have_ref():
+        pytest.skip("oracle/_ref/libkblas_ref.so not built (needs /root/reference at build time)")
+    kb, h, torch = env
+    dt = DT[p]
+    ct = C.c_double if p == "D" else C.c_float
+    ref = U.RefLib()
+    H, i, l, c, P = ref.H, ref.i, ref.l, ref.c, ref.P
+    r_potrf = ref.fn(f"kblas{p}potrf_batch_strided", [H, c, i, P, i, l, i, P])
+    r_potrs = ref.fn(f"kblas{p}potrs_batch_strided", [H, c, c, i, i, P, i, l, P, i, l, i])
+    r_trsm = ref.fn(f"kblas{p}trsm_batch_strided", [H, c, c, c, c, i, i, ct, P, i, l, P, i, l, i])
+    batch = 4099
+    for n in (8, 16, 24, 32):
+        m = n
+        A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n)
+        B0 = U.rand_batch(batch, m, n, dtype=dt, seed=n + 1)
+        mine_A, ref_A = _dev(torch, A0), _dev(torch, A0)
+        mine_B, ref_B = _dev(torch, B0), _dev(torch, B0)
+        mine_T, ref_T = _dev(torch, B0), _dev(torch, B0)
+        info_m = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+        info_r = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+        ref.wsquery("kblas_posv_batch_strided_wsquery", "ciii", b"R", m, n, batch)
+        ref.wsquery("kblas_trsm_batch_strided_wsquery", "ciii", b"L", m, n, batch)
+        ref.allocate()
+        h.posv_batch_strided_wsquery("R", m, n, batch)
+        h.allocate_workspace()
+        rc_r = r_potrf(ref.h, b"L", n, ref_A.data_ptr(), n, n * n, batch, info_r.data_ptr())
+        rc_m = h.potrf_batch_strided("L", n, mine_A, n, n * n, batch, info_m)
+        assert rc_r == rc_m == 1
+        rc_r = r_potrs(ref.h, b"R", b"L", m, n, ref_A.data_ptr(), n, n * n, ref_B.data_ptr(), m, m * n, batch)
+        rc_m = h.potrs_batch_strided("R", "L", m, n, ref_A, n, n * n, mine_B, m, m * n, batch)
+        assert rc_r == rc_m == 1
+        rc_r = r_trsm(ref.h, b"L", b"L", b"N", b"N", m, n, 0.28, ref_A.data_ptr(), n, n * n, ref_T.data_ptr(), m, m * n, batch)
+        rc_m = h.trsm_batch_strided("L", "L", "N", "N", m, n, 0.28, ref_A, n, n * n, mine_T, m, m * n, batch)
+        assert rc_r == rc_m == 1
+        torch.cuda.synchronize()
+        _check_potrf(A0, mine_A.cpu().numpy(), n, dt, Lref=ref_A.cpu().numpy())
+        assert torch.equal(info_m, info_r)
+        for mine, theirs in ((mine_B, ref_B), (mine_T, ref_T)):
+            t = theirs.cpu().numpy()
+            assert np.abs(mine.cpu().numpy() - t).max() <= 100 * n * U.EPS[dt] * max(1.0, np.abs(t).max())
+    ref.close()
+
+
+# =============================================================================================
+# BASELINE.json full sizes through size-independent properties
+@pytest.mark.parametrize("p,n,batch", [("D", 32, 1 << 20), ("D", 8, 1 << 20), ("D", 16, 1 << 20), ("D", 24, 1 << 20), ("S", 32, 1 << 20)])
+def test_full_size_potrf_potrs_properties(env, p, n, batch):
+    """config 2: strided potrf + potrs, batch = 1M.  Checked by residual / solve-residual on slices
+    spread over the batch (first, middle, last CTAs) and by finiteness + untouched upper over all of it."""
+    kb, h, torch = env
+    tdt = torch.float64 if p == "D" else torch.float32
+    eps = U.EPS[DT[p]]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdt)
+    A = torch.tril(A) + torch.tril(A, -1).transpose(1, 2)
+    A.diagonal(dim1=1, dim2=2).add_(n)
+    A0 = A.clone()
+    B = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdt)   # m = n right-hand-side rows
+    B0 = B.clone()
+    h.posv_batch_strided_wsquery("R", n, n, batch)
+    h.allocate_workspace()
+    assert h.potrf_batch_strided("L", n, A, n, n * n, batch, None) == kb.KBLAS_Success
+    assert h.potrs_batch_strided("R", "L", n, n, A, n, n * n, B, n, n * n, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(A).all()) and bool(torch.isfinite(B).all())
+    # memory layout [b, col, row]: the strict upper triangle of the matrix is torch's strict LOWER of A[b]
+    assert torch.equal(torch.tril(A, -1), torch.tril(A0, -1)), "strict upper triangle modified"
+    for lo in (0, batch // 2 - 2048, batch - 4096):
+        sl = slice(lo, lo + 4096)
+        Lm = torch.triu(A[sl]).transpose(1, 2).double()          # math-layout lower factor
+        Am = A0[sl].transpose(1, 2).double()
+        R = Am - Lm @ Lm.transpose(1, 2)
+        res = (R.flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
+        assert res <= 10 * n * eps, (lo, res)
+        Xm, Bm = B[sl].transpose(1, 2).double(), B0[sl].transpose(1, 2).double()
+        R2 = Xm @ Am - Bm                                          # X A = B
+        res2 = (R2.flatten(1).norm(dim=1) / (Am.flatten(1).norm(dim=1) * Xm.flatten(1).norm(dim=1))).max().item()
+        assert res2 <= 10 * n * eps, (lo, res2)
+
+
+def test_multi_stream_and_timer(env):
+    kb, h, torch = env
+    s = torch.cuda.Stream()
+    h.set_stream(s)
+    assert h.get_stream() == s.cuda_stream
+    n, batch = 32, 5000
+    A0 = U.rand_spd_batch(batch, n, seed=4)
+    dA = _dev(torch, A0)
+    s.wait_stream(torch.cuda.current_stream())
+    h.timer_tic()
+    assert h.potrf_batch_strided("L", n, dA, n, n * n, batch, None) == kb.KBLAS_Success
+    h.timer_record_end()
+    sec = h.timer_toc()
+    assert 0 < sec < 1.0
+    s.synchronize()
+    Lo = A0.copy()
+    U.oracle_potrf(Lo, n)
+    _check_potrf(A0, dA.cpu().numpy(), n, np.float64, Lref=Lo)
+    h.set_stream(0)

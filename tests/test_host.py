@@ -1,0 +1,158 @@
+"""CPU: host-side logic and the C ABI surface (no compute calls, no GPU needed)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests import _util as U
+
+
+def _declared_c_symbols():
+    """every function name the plain-C FFI header declares (after preprocessing)"""
+    inc = os.path.join(U.ROOT, "include")
+    src = subprocess.check_output(["gcc", "-E", "-P", "-x", "c", os.path.join(inc, "kblas_ffi.h")], text=True)
+    names = set(re.findall(r"\b(kblas\w*)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_loads_and_exports_every_declared_symbol(built):
+    kb = U.kblas()
+    lib = C.CDLL(kb.LIB_PATH)
+    names = _declared_c_symbols()
+    assert len(names) >= 50
+    for fam in ("potrf", "trsm", "potrs", "posv"):
+        for p in "SD":
+            assert f"kblas{p}{fam}_batch" in names and f"kblas{p}{fam}_batch_strided" in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_mangled_cpp_symbols_match_the_reference_abi(built):
+    """code compiled against the reference headers links unchanged: same mangled names
+    (reference include/kblas.h:54-108, kblas_batch.h wsquery + overloads, Xhelper_funcs.ch:48-55)"""
+    kb = U.kblas()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", kb.LIB_PATH], text=True)
+    ours = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    want = [
+        U.mangle("kblasCreate", ["HH"]), U.mangle("kblasDestroy", ["HH"]),
+        U.mangle("kblasAllocateWorkspace", ["H"]), U.mangle("kblasFreeWorkspace", ["H"]),
+        U.mangle("kblasTimerTic", ["H"]), U.mangle("kblasTimerRecordEnd", ["H"]), U.mangle("kblasTimerToc", ["H"]),
+        U.mangle("kblasCreateStreams", ["H", "i"]), U.mangle("kblasGetStream", ["H"]),
+        U.mangle("kblasGetCublasHandle", ["H"]), U.mangle("kblasGetErrorString", ["i"]),
+        "_Z14kblasSetStreamP11KBlasHandleP11CUstream_st",
+        U.mangle("kblas_potrf_batch_wsquery", ["H", "i", "i"]),
+        U.mangle("kblas_potrf_batch_strided_wsquery", ["H", "i", "i"]),
+        U.mangle("kblas_trsm_batch_wsquery", ["H", "c", "i", "i", "i"]),
+        U.mangle("kblas_trsm_batch_strided_wsquery", ["H", "c", "i", "i", "i"]),
+        U.mangle("kblas_potrs_batch_wsquery", ["H", "i", "i", "i"]),
+        U.mangle("kblas_potrs_batch_strided_wsquery", ["H", "i", "i", "i"]),
+        U.mangle("kblas_posv_batch_wsquery", ["H", "c", "i", "i", "i"]),
+        U.mangle("kblas_posv_batch_strided_wsquery", ["H", "c", "i", "i", "i"]),
+        "_Z17kblas_potrf_batchP11KBlasHandleciPdiliPi", "_Z17kblas_potrf_batchP11KBlasHandleciPPdiiPi",
+        "_Z17kblas_potrf_batchP11KBlasHandleciPfiliPi", "_Z17kblas_potrf_batchP11KBlasHandleciPPfiiPi",
+        "_Z14Xset_pointer_1PPdPKdillP11CUstream_st", "_Z14Xset_pointer_1PPfPKfillP11CUstream_st",
+        "_Z12iset_value_1PiilP11CUstream_st", "_Z8REG_SIZEi", "_Z16CLOSEST_REG_SIZEi",
+    ]
+    missing = [w for w in want if w not in ours]
+    assert not missing, missing
+    if U.have_ref():
+        out = subprocess.check_output(["nm", "-D", "--defined-only", U.REF_SO], text=True)
+        theirs = {l.split()[-1] for l in out.splitlines() if l.strip()}
+        hot = [s for s in theirs if re.search(r"kblas_?(potrf|trsm|potrs|posv)_batch|kblas[SD](potrf|trsm|potrs|posv)_batch", s)
+               and "core" not in s and "offset" not in s and "Xtrsm" not in s and "nonuniform" not in s
+               and not re.search(r"(PPi|Pii|PiS)", s)      # non-uniform overloads (MAGMA-only path, out of scope)
+               and "cuComplex" not in s and "6float2" not in s and "7double2" not in s]
+        absent = sorted(s for s in hot if s not in ours)
+        assert not absent, absent
+
+
+def test_return_code_constants_and_error_strings(built):
+    kb = U.kblas()
+    assert (kb.KBLAS_Success, kb.KBLAS_UnknownError, kb.KBLAS_NotImplemented, kb.KBLAS_InsufficientWorkspace) == (1, 0, -2, -6)
+    assert kb.error_string(-6) == "Insufficient workspace supplied to function"   # kblas_common.cu:185
+    assert kb.error_string(-2) == "Operation not implemented yet"
+    assert kb.error_string(12345) == "unknown KBLAS error code"
+    assert kb.roundup(33, 32) == 64 and kb.roundup(32, 32) == 32
+
+
+def test_reg_size_rules(built):
+    kb = U.kblas()
+    # reference src/kblas_common.cu:241-255
+    assert [kb.reg_size(n) for n in (0, 1, 2, 3, 16, 24, 32)] == [False, True, True, False, True, False, True]
+    assert [kb.closest_reg_size(n) for n in (0, 1, 2, 3, 16, 17, 24, 32, 33, 100, 256)] == [0, 0, 1, 2, 8, 16, 16, 16, 32, 64, 128]
+
+
+def _ref_potrf_ws(strided, n, batch):
+    """restatement of workspace_queries.ch:111-122 + .cu:188-238 for the d_ptrs region"""
+    def clos(x):
+        r = 1
+        while r < x:
+            r <<= 1
+        return r >> 1 if x > 0 else 0
+    n1 = clos(n)
+    need = 0
+    if n1 > 16 and not strided:      # trsm(R, m = n-n1, n = n1) recursion -> offset GEMM pointer triples
+        need = max(need, (batch > 1) * batch * 24)
+    m = n - n1
+    if m > 16:                        # syrk pointer triples, both modes
+        depth, s = 0, 16
+        while s < m:
+            s <<= 1
+            depth += 1
+        need = max(need, (1 << (depth - 1)) * batch * 24)
+    return need
+
+
+@pytest.mark.parametrize("strided", [True, False])
+@pytest.mark.parametrize("n", [8, 16, 24, 32, 33, 64, 100, 128, 256])
+def test_potrf_wsquery_bytes(built, strided, n):
+    kb = U.kblas()
+    batch = 1000
+    assert kb.wsquery_bytes("potrf", strided, 0, n, batch) == (0, 0, 0, _ref_potrf_ws(strided, n, batch))
+
+
+def test_wsquery_headline_configs(built):
+    kb = U.kblas()
+    # strided potrf/trsm/potrs n<=32 -> 0 B; config 4 (ptr posv n=256, 64K) -> 6.3 MB d_ptrs
+    assert kb.wsquery_bytes("potrf", True, 0, 32, 1 << 20) == (0, 0, 0, 0)
+    assert kb.wsquery_bytes("trsm", True, 32, 32, 1 << 20, side="L") == (0, 0, 0, 0)
+    assert kb.wsquery_bytes("potrs", True, 32, 32, 1 << 20) == (0, 0, 0, 0)
+    assert kb.wsquery_bytes("posv", False, 16, 256, 1 << 16) == (0, 0, 0, 6291456)
+    assert kb.wsquery_bytes("potrs", False, 16, 8, 100) == (0, 0, 0, 2400)      # offset GEMM even for n <= 16
+    assert kb.wsquery_bytes("trsm", False, 32, 8, 100, side="R") == (0, 0, 0, 0)
+    assert kb.wsquery_bytes("trsm", False, 32, 8, 100, side="L") == (0, 0, 0, 2400)
+    assert kb.wsquery_bytes("trsm", False, 32, 8, 1, side="L") == (0, 0, 0, 0)    # (batchCount > 1) factor
+
+
+def test_slab_partition():
+    kb = U.kblas()
+    slab = __import__("importlib").import_module("kblas-gpu_b200.slab")
+    for batch, world in ((1 << 23, 8), (10, 4), (7, 8), (0, 2), (1000003, 3)):
+        cover = []
+        for r in range(world):
+            b, e = slab.slab_range(batch, world, r)
+            assert 0 <= b <= e <= batch
+            cover += list(range(b, e)) if batch < 100 else []
+            if r:
+                assert b == slab.slab_range(batch, world, r - 1)[1]
+        assert slab.slab_range(batch, world, world - 1)[1] == batch
+        if batch < 100:
+            assert cover == list(range(batch))
+    assert slab.slab_offsets(1 << 23, 8, 3, 1024, 8) == (3 << 20, 1 << 20, (3 << 20) * 8192)
+    assert kb is not None
+
+
+def test_product_does_not_touch_the_oracle():
+    """the shipped package must never import, link or fall back to oracle/ (tier rule 3)"""
+    pkg = os.path.join(U.ROOT, "kblas-gpu_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) in ("build", "lib"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt, (dirpath, f)
+    out = subprocess.check_output(["ldd", U.kblas().LIB_PATH], text=True)
+    assert "oracle" not in out and "openblas" not in out and "cublas" not in out
