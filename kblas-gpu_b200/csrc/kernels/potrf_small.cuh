@@ -12,7 +12,7 @@
 // the 496 of a row-per-lane layout.
 //
 // Right-looking column step j (same recurrence as Xpotrf_batch_kernels.cuh:50-69):
-//   d = A[j][j] (width-G shuffle), r = 1/sqrt(d), column j *= r, publish column j through a
+//   d = A[j][j] (width-G shuffle), r = rsqrt(d), column j *= r, publish column j through a
 //   double-buffered shared-memory line, every lane reads L[k][j] (k > j) back as broadcast
 //   128-bit loads and applies  A[i][k] -= L[i][j] * L[k][j]  to the rows it owns.
 // Shared memory replaces the reference's per-element __shfl broadcast (2 SHFL per fp64 value,
@@ -26,9 +26,24 @@
 // n < NP is handled by padding with the identity in registers.
 #pragma once
 
+#include <cstdint>
 #include "common.cuh"
 
 namespace kblasx {
+
+// L2 prefetch of the lower triangle of one matrix: lane = column, the 128-byte lines spanning rows
+// [col, n) of that column (DRAM reads are line granular on B200, profiles/r01_dram_granularity.md).
+template <typename T>
+__device__ __forceinline__ void prefetch_lower_l2(const T *A, int n, int lda, int lane) {
+  if (lane < n) {
+    const char *p0 = reinterpret_cast<const char *>(A + lane + (long)lane * lda);
+    const char *p1 = reinterpret_cast<const char *>(A + (n - 1) + (long)lane * lda);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
+    if ((reinterpret_cast<uintptr_t>(p1) >> 7) != (reinterpret_cast<uintptr_t>(p0) >> 7))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+    if (p1 - p0 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 128));
+  }
+}
 
 template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
@@ -49,85 +64,104 @@ potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const in
   const int warp = threadIdx.x >> 5;
   const int l = lane % G;
   const int g = lane / G;
-  const long mat = ((long)blockIdx.x * WARPS + warp) * MPW + g;
-  const bool active = mat < (long)batchCount;
-  T *__restrict__ A = active ? Aref.at(mat) : nullptr;
-
-#define KX_IDX(s_, c_) (G * (((s_) * ((s_) + 1)) / 2) + (c_))
-  T a[G * (S * (S + 1)) / 2];
-
-  // ---- load the lower triangle (whole sectors only) ---------------------------------------
-#pragma unroll
-  for (int col = 0; col < NP; ++col) {
-    const T *pc = A + l + (long)col * lda;
-#pragma unroll
-    for (int s = col / G; s < S; ++s) {
-      const int row = G * s + l;
-      const bool inside = (row < n) && (col < n);
-      const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
-      T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
-      if (active && inside && need) v = ldg_stream(pc + G * s);
-      a[KX_IDX(s, col)] = v;
-    }
-  }
-
-  int bad = 0;
   T *const wbase = bc + warp * (2 * BUF_STRIDE) + g * 2;
 
-  // ---- right-looking factorisation ---------------------------------------------------------
-#pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    const int t = j / G, c = j % G;
-    const T d = shfl_seg<G>(a[KX_IDX(t, j)], c);
-    if (info_mode) {
-      if (bad == 0 && j < n && !(d > T(0))) bad = j + 1;
-    }
-    const T r = T(1) / sqrt_t(d);
-#pragma unroll
-    for (int s = t; s < S; ++s) a[KX_IDX(s, j)] *= r;
+  // persistent warps: warp-batch wb covers matrices [wb*MPW, wb*MPW + MPW)
+  const long nwb = ((long)batchCount + MPW - 1) / MPW;
+  const long wstride = (long)gridDim.x * WARPS;
+  for (long wb = (long)blockIdx.x * WARPS + warp; wb < nwb; wb += wstride) {
+    const long mat = wb * MPW + g;
+    const bool active = mat < (long)batchCount;
+    T *__restrict__ A = active ? Aref.at(mat) : nullptr;
 
-    if (j + 1 < NP) {
-      T *wb = wbase + (j & 1) * BUF_STRIDE;
-      // publish column j (rows of every slot that still reaches below the diagonal)
+#define KX_IDX(s_, c_) (G * (((s_) * ((s_) + 1)) / 2) + (c_))
+    T a[G * (S * (S + 1)) / 2];
+
+    // ---- load the lower triangle (whole sectors only) -------------------------------------
 #pragma unroll
-      for (int s = t; s < S; ++s) {
-        if (G * s + G - 1 > j) {
-          const int k = G * s + l;
-          wb[(k >> 1) * PAIR + (k & 1)] = a[KX_IDX(s, j)];
+    for (int col = 0; col < NP; ++col) {
+      const T *pc = A + l + (long)col * lda;
+#pragma unroll
+      for (int s = col / G; s < S; ++s) {
+        const int row = G * s + l;
+        const bool inside = (row < n) && (col < n);
+        const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
+        T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
+        if (active && inside && need) v = ldg_stream(pc + G * s);
+        a[KX_IDX(s, col)] = v;
+      }
+    }
+
+    // ---- pull the NEXT warp-batch of this warp into L2 while this one is being factored ----
+    {
+      const long nb = wb + wstride;
+#pragma unroll
+      for (int q = 0; q < MPW; ++q) {
+        const long m2 = nb * MPW + q;
+        if (nb < nwb && m2 < (long)batchCount) prefetch_lower_l2<T>(Aref.at(m2), n, lda, lane);
+      }
+    }
+
+    int bad = 0;
+
+    // ---- right-looking factorisation -------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int t = j / G, c = j % G;
+      const T d = shfl_seg<G>(a[KX_IDX(t, j)], c);
+      if (info_mode) {
+        if (bad == 0 && j < n && !(d > T(0))) bad = j + 1;
+      }
+      const T r = rsqrt_t(d);
+#pragma unroll
+      for (int s = t; s < S; ++s) a[KX_IDX(s, j)] *= r;
+
+      if (j + 1 < NP) {
+        T *wbuf = wbase + (j & 1) * BUF_STRIDE;
+        // publish column j (rows of every slot that still reaches below the diagonal)
+#pragma unroll
+        for (int s = t; s < S; ++s) {
+          if (G * s + G - 1 > j) {
+            const int k = G * s + l;
+            wbuf[(k >> 1) * PAIR + (k & 1)] = a[KX_IDX(s, j)];
+          }
+        }
+        __syncwarp();
+        // trailing update: A[i][k] -= L[i][j] * L[k][j] for every owned row i >= k > j.
+        // Rows above the diagonal inside the diagonal slot pick up garbage that is never
+        // published, read or stored (same as the reference's unguarded register updates).
+#pragma unroll
+        for (int p = (j + 1) / 2; p < NP / 2; ++p) {
+          const V2 v2 = *reinterpret_cast<const V2 *>(wbuf + p * PAIR);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * p + h;
+            if (k > j) {
+              const T v = h ? v2.y : v2.x;
+#pragma unroll
+              for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
+            }
+          }
         }
       }
-      __syncwarp();
-      // trailing update: A[i][k] -= L[i][j] * L[k][j] for every owned row i >= k > j.
-      // Rows above the diagonal inside the diagonal slot pick up garbage that is never
-      // published, read or stored (same as the reference's unguarded register updates).
+
+      // ---- store a finished block of G columns as soon as it is final (spreads the stores) ----
+      if (c == G - 1) {
 #pragma unroll
-      for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-        const V2 v2 = *reinterpret_cast<const V2 *>(wb + p * PAIR);
+        for (int col = j - (G - 1); col <= j; ++col) {
+          T *pc = A + l + (long)col * lda;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = 2 * p + h;
-          if (k > j) {
-            const T v = h ? v2.y : v2.x;
-#pragma unroll
-            for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
+          for (int s = col / G; s < S; ++s) {
+            const int row = G * s + l;
+            if (active && row >= col && row < n) stg_stream(pc + G * s, a[KX_IDX(s, col)]);
           }
         }
       }
     }
-  }
-
-  // ---- store the lower triangle ------------------------------------------------------------
-#pragma unroll
-  for (int col = 0; col < NP; ++col) {
-    T *pc = A + l + (long)col * lda;
-#pragma unroll
-    for (int s = col / G; s < S; ++s) {
-      const int row = G * s + l;
-      if (active && row >= col && row < n) stg_stream(pc + G * s, a[KX_IDX(s, col)]);
-    }
-  }
-  if (info_mode && active && l == 0) info[mat] = bad;
+    if (info_mode && active && l == 0) info[mat] = bad;
+    __syncwarp();  // the broadcast buffers are reused by the next warp-batch
 #undef KX_IDX
+  }
 }
 
 }  // namespace kblasx

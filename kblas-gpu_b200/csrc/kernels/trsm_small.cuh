@@ -28,6 +28,14 @@ namespace kblasx {
 
 enum TriOp { TRI_FORWARD = 0, TRI_BACKWARD = 1, TRI_BOTH = 2 };
 
+// ptxas hoists the (volatile) shared-memory loads of later columns far ahead of the FMAs that
+// consume them; unbounded, that costs > 200 registers or even kilobytes of spills for the fused
+// forward+backward solve.  A warp-level sync every KX_TRI_FENCE columns bounds the look-ahead.
+#ifndef KX_TRI_FENCE
+#define KX_TRI_FENCE 8
+#endif
+__device__ __forceinline__ void sched_fence() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); }
+
 // Stage the k x k lower factor of one matrix into shared memory: Ls[row + col*NP], padded
 // with the identity; invd[j] = 1 / L_jj.  One warp, coalesced column reads.
 template <typename T, int NP>
@@ -55,11 +63,12 @@ __device__ __forceinline__ void tri_forward(T (&x)[NP], const T *__restrict__ Ls
   typedef typename Vec2T<T>::type V2;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    x[j] *= invd[j];
+    if (j % KX_TRI_FENCE == 0) sched_fence();
+    x[j] *= lds_one(invd + j);
     const T nx = -x[j];
 #pragma unroll
     for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-      const V2 l2 = *reinterpret_cast<const V2 *>(Ls + 2 * p + j * NP);
+      const V2 l2 = lds_pair(Ls + 2 * p + j * NP);
       if (2 * p > j) x[2 * p] = fma_t(nx, l2.x, x[2 * p]);
       x[2 * p + 1] = fma_t(nx, l2.y, x[2 * p + 1]);
     }
@@ -72,14 +81,15 @@ __device__ __forceinline__ void tri_backward(T (&x)[NP], const T *__restrict__ L
   typedef typename Vec2T<T>::type V2;
 #pragma unroll
   for (int j = NP - 1; j >= 0; --j) {
+    if (j % KX_TRI_FENCE == KX_TRI_FENCE - 1) sched_fence();
     T acc0 = x[j], acc1 = T(0);
 #pragma unroll
     for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-      const V2 l2 = *reinterpret_cast<const V2 *>(Ls + 2 * p + j * NP);
+      const V2 l2 = lds_pair(Ls + 2 * p + j * NP);
       if (2 * p > j) acc0 = fma_t(-x[2 * p], l2.x, acc0);
       acc1 = fma_t(-x[2 * p + 1], l2.y, acc1);
     }
-    x[j] = (acc0 + acc1) * invd[j];
+    x[j] = (acc0 + acc1) * lds_one(invd + j);
   }
 }
 
@@ -95,7 +105,7 @@ struct TriSmem {
 // k = order of the triangular factor (n for side R, m for side L); vec = the other dimension
 // of B (number of independent vectors).  OP selects forward / backward / both (potrs).
 template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, LEFT ? 3 : 4)
 tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                        BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

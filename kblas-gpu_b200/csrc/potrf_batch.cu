@@ -6,6 +6,7 @@
 #include "kblas.h"
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
+#include "kernels/potrf_panel.cuh"
 #include "potrf_batch.h"
 
 namespace kblasx {
@@ -15,7 +16,16 @@ static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T,
                             int *info) {
   constexpr int MPW = 32 / G;
   const long per_cta = (long)WARPS * MPW;
-  const long grid = (batchCount + per_cta - 1) / per_cta;
+  // persistent warps: one wave of CTAs (MINB per SM), each warp strides over its warp-batches
+  const long need = (batchCount + per_cta - 1) / per_cta;
+  static int ctas_per_sm = 0;  // per instantiation
+  if (ctas_per_sm == 0) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED>, WARPS * 32, 0);
+    ctas_per_sm = occ > 0 ? occ : MINB;
+  }
+  const long wave = (long)h->sm_count * ctas_per_sm;
+  const long grid = need < wave ? need : wave;
   potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED>
       <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
   h->note_launch(name);
@@ -35,11 +45,39 @@ static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
   if (n <= 8) return KX_LAUNCH_REG(8, 8, 4, 4);
   if (n <= 16) return KX_LAUNCH_REG(16, 8, 4, 4);
   if (n <= 24) return KX_LAUNCH_REG(24, 8, 4, 3);
-  switch (v) {
-    case 1: return KX_LAUNCH_REG(32, 16, 4, 3);
-    case 2: return KX_LAUNCH_REG(32, 8, 5, 2);
-    default: return KX_LAUNCH_REG(32, 8, 4, 2);
+  if constexpr (sizeof(T) == 4) {
+    // fp32: 80 values per lane fit a 128-register budget -> 16 resident warps per SM
+    switch (v) {
+      case 1: return KX_LAUNCH_REG(32, 16, 4, 4);
+      case 2: return KX_LAUNCH_REG(32, 8, 4, 2);
+      default: return KX_LAUNCH_REG(32, 8, 4, 4);
+    }
+  } else {
+    switch (v) {
+      case 1: return KX_LAUNCH_REG(32, 16, 4, 3);
+      case 2: return KX_LAUNCH_REG(32, 8, 5, 2);
+      default: return KX_LAUNCH_REG(32, 8, 4, 2);
+    }
   }
+}
+
+// n > 32: one CTA per matrix, left-looking 32-column panels (kernels/potrf_panel.cuh)
+template <typename T, int THREADS, bool STRIDED>
+static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
+                              int *info) {
+  potrf_panel_kernel<T, THREADS, STRIDED><<<(unsigned)batchCount, THREADS, 0, h->stream>>>(n, A, lda, batchCount, info,
+                                                                                            h->info_mode);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+template <typename T, bool STRIDED>
+static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
+  // THREADS*2 rows per slab: pick the smallest CTA that covers the first panel in one slab
+  if (n <= 64) return launch_potrf_panel<T, 32, STRIDED>(h, "potrf_panel<T=32>", n, A, lda, batchCount, info);
+  if (n <= 128) return launch_potrf_panel<T, 64, STRIDED>(h, "potrf_panel<T=64>", n, A, lda, batchCount, info);
+  return launch_potrf_panel<T, 128, STRIDED>(h, "potrf_panel<T=128>", n, A, lda, batchCount, info);
 }
 
 // Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)
@@ -55,7 +93,7 @@ int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, i
   }
   if (n <= 0) return KBLAS_Success;  // reference launches a kernel that does nothing
   if (n <= 32) return potrf_small_dispatch<T, STRIDED>(h, n, A, lda, batchCount, info);
-  return KBLAS_NotSupported;
+  return potrf_panel_dispatch<T, STRIDED>(h, n, A, lda, batchCount, info);
 }
 
 template int potrf_batch_core<float, true>(KBlasHandle *, char, int, BatchRef<float, true>, int, int, int *);

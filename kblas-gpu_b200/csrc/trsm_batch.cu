@@ -6,6 +6,7 @@
 #include "kblas.h"
 #include "kblas_common.h"
 #include "kernels/trsm_small.cuh"
+#include "kernels/trsm_blocked.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -31,6 +32,21 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
   return KBLAS_Success;
 }
 
+// k > 32: blocked substitution, one warp per (matrix, 32-vector slab) (kernels/trsm_blocked.cuh)
+template <typename T, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                              BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = sizeof(T) == 8 ? 2 : 4;  // 16.5 KB (fp64) / 8.3 KB (fp32) of shared memory per warp
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  tri_solve_blocked_kernel<T, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch("tri_blocked");
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
@@ -49,9 +65,10 @@ int tri_solve_core(KBlasHandle *h, bool left, int op, int m, int n, T alpha, Bat
   if (batchCount <= 0) {
     check_error_ret(cudaErrorInvalidConfiguration, KBLAS_UnknownError);  // reference: empty grid
   }
-  if (k > 32) return KBLAS_NotSupported;
   if (vec <= 0) return KBLAS_Success;
-#define KX_TRI(L_, O_) tri_small_np<T, L_, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount)
+#define KX_TRI(L_, O_)                                                                              \
+  (k <= 32 ? tri_small_np<T, L_, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount)          \
+           : launch_tri_blocked<T, L_, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount))
   if (left) {
     if (op == TRI_FORWARD) return KX_TRI(true, TRI_FORWARD);
     if (op == TRI_BACKWARD) return KX_TRI(true, TRI_BACKWARD);
