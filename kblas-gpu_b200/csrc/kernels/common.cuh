@@ -40,6 +40,16 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
   asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+// predicated forms: a real predicated LDG (no branch, no convergence barrier), so that a whole
+// batch of loads can be in flight before the first use; `v` keeps its value when pred is false.
+__device__ __forceinline__ void ldg_stream_if(double &v, const double *p, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.global.L1::no_allocate.f64 %0, [%1]; }"
+               : "+d"(v) : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldg_stream_if(float &v, const float *p, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.global.L1::no_allocate.f32 %0, [%1]; }"
+               : "+f"(v) : "l"(p), "r"((int)pred));
+}
 __device__ __forceinline__ void stg_stream(double *p, double v) {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }

@@ -23,7 +23,11 @@
 // Sectors that lie entirely in the strict upper triangle are never loaded, and only
 // elements with row >= col are stored: the strict upper triangle is bit-preserved, as in
 // the reference (stores guarded by tx >= i, Xpotrf_batch_kernels.cuh:73-77).
-// n < NP is handled by padding with the identity in registers.
+// Persistent CTAs walk the batch; while one warp-batch is being factored the next one is pulled
+// into L2 (prefetch.global.L2), and finished block columns are stored as soon as they are final.
+// The whole column loop is unrolled (register indexing), ~45 KB of code: the warps of a CTA are
+// re-aligned once per warp-batch (LOCKSTEP) so that they share instruction-cache lines.
+// n < NP is handled by padding with the identity in registers (EXACT = false).
 #pragma once
 
 #include <cstdint>
@@ -45,76 +49,96 @@ __device__ __forceinline__ void prefetch_lower_l2(const T *A, int n, int lda, in
   }
 }
 
-template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED>
+// EXACT: n == NP (no bounds predicates, no info support); LOCKSTEP: __syncthreads per warp-batch.
+// With EXACT the stores are SECTOR granular: a 32-byte sector that straddles the diagonal is written
+// back whole, its strict-upper elements carrying the very bits that were loaded (the register
+// updates are predicated so they never touch them).  Partially written sectors cost an L2
+// read-modify-write fill each; measured on B200 (tools/microbench_pattern.cu) the pure access
+// pattern runs at 3.19 ms / 2^20 matrices with element-exact stores and 2.23 ms with whole sectors.
+template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED, bool EXACT, bool LOCKSTEP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
-                 const int info_mode) {
-  constexpr int S = NP / G;     // row slots per lane
-  constexpr int MPW = 32 / G;   // matrices per warp
+potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount,
+                 int *__restrict__ info, const int info_mode_arg) {
+  constexpr int S = NP / G;                    // row slots per lane
+  constexpr int MPW = 32 / G;                  // matrices per warp
+  constexpr int GH = (16 / G) > 0 ? (16 / G) : 1;  // lane groups per half-warp
   constexpr int SE = SectorElems<T>::value;
-  constexpr int PAIR = MPW * 2;                 // elements per row pair in the broadcast line
-  constexpr int BUF_STRIDE = (NP / 2) * PAIR;   // elements per buffer
+  // broadcast line of one buffer: [group / GH][row pair][group % GH][2]  -- the 16 lanes of a
+  // half-warp write 128 contiguous bytes (conflict-free STS.64), a group reads 16-byte pairs
+  constexpr int PAIR = GH * 2;
+  constexpr int BUF_STRIDE = (NP / 2) * MPW * 2;  // elements per buffer
   typedef typename Vec2T<T>::type V2;
   static_assert(NP % G == 0 && G % 2 == 0 && 32 % G == 0, "bad tiling");
 
-  // broadcast line: [warp][buffer][row pair][matrix in warp][2]
   __shared__ __align__(16) T bc[WARPS * 2 * BUF_STRIDE];
 
+  const int n = EXACT ? NP : n_arg;
+  const int info_mode = EXACT ? 0 : info_mode_arg;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int l = lane % G;
   const int g = lane / G;
-  T *const wbase = bc + warp * (2 * BUF_STRIDE) + g * 2;
+  T *const wbase = bc + warp * (2 * BUF_STRIDE) + (g / GH) * ((NP / 2) * PAIR) + (g % GH) * 2;
 
-  // persistent warps: warp-batch wb covers matrices [wb*MPW, wb*MPW + MPW)
+  // persistent CTAs: CTA-batch cb covers warp-batches [cb*WARPS, cb*WARPS + WARPS), a warp-batch
+  // covers matrices [wb*MPW, wb*MPW + MPW)
   const long nwb = ((long)batchCount + MPW - 1) / MPW;
-  const long wstride = (long)gridDim.x * WARPS;
-  for (long wb = (long)blockIdx.x * WARPS + warp; wb < nwb; wb += wstride) {
+  const long ncb = (nwb + WARPS - 1) / WARPS;
+  for (long cb = blockIdx.x; cb < ncb; cb += gridDim.x) {
+    if (LOCKSTEP) __syncthreads();
+    const long wb = cb * WARPS + warp;
     const long mat = wb * MPW + g;
     const bool active = mat < (long)batchCount;
-    T *__restrict__ A = active ? Aref.at(mat) : nullptr;
+    // inactive groups factor a copy of the last matrix (never stored): keeps the loads unpredicated
+    T *__restrict__ A = Aref.at(active ? mat : (long)batchCount - 1);
 
 #define KX_IDX(s_, c_) (G * (((s_) * ((s_) + 1)) / 2) + (c_))
     T a[G * (S * (S + 1)) / 2];
 
     // ---- load the lower triangle (whole sectors only) -------------------------------------
+    {
+      const T *pc = A + l;
 #pragma unroll
-    for (int col = 0; col < NP; ++col) {
-      const T *pc = A + l + (long)col * lda;
+      for (int col = 0; col < NP; ++col) {
 #pragma unroll
-      for (int s = col / G; s < S; ++s) {
-        const int row = G * s + l;
-        const bool inside = (row < n) && (col < n);
-        const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
-        T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
-        if (active && inside && need) v = ldg_stream(pc + G * s);
-        a[KX_IDX(s, col)] = v;
+        for (int s = col / G; s < S; ++s) {
+          const int row = G * s + l;
+          const bool inside = EXACT || ((row < n) && (col < n));
+          const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
+          T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
+          if (inside && need) v = ldg_stream(pc + G * s);
+          a[KX_IDX(s, col)] = v;
+        }
+        pc += lda;
       }
     }
 
     // ---- pull the NEXT warp-batch of this warp into L2 while this one is being factored ----
     {
-      const long nb = wb + wstride;
+      const long nb = wb + (long)gridDim.x * WARPS;
 #pragma unroll
       for (int q = 0; q < MPW; ++q) {
         const long m2 = nb * MPW + q;
-        if (nb < nwb && m2 < (long)batchCount) prefetch_lower_l2<T>(Aref.at(m2), n, lda, lane);
+        if (m2 < (long)batchCount) prefetch_lower_l2<T>(Aref.at(m2), n, lda, lane);
       }
     }
 
     int bad = 0;
+    T *pst = A + l;  // column pointer of the next block of columns to store
 
     // ---- right-looking factorisation -------------------------------------------------------
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const int t = j / G, c = j % G;
       const T d = shfl_seg<G>(a[KX_IDX(t, j)], c);
-      if (info_mode) {
+      if (!EXACT && info_mode) {
         if (bad == 0 && j < n && !(d > T(0))) bad = j + 1;
       }
       const T r = rsqrt_t(d);
 #pragma unroll
-      for (int s = t; s < S; ++s) a[KX_IDX(s, j)] *= r;
+      for (int s = t; s < S; ++s) {
+        if (!EXACT || s > t || l >= c) a[KX_IDX(s, j)] *= r;  // EXACT: keep the upper elements intact
+      }
 
       if (j + 1 < NP) {
         T *wbuf = wbase + (j & 1) * BUF_STRIDE;
@@ -128,8 +152,8 @@ potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const in
         }
         __syncwarp();
         // trailing update: A[i][k] -= L[i][j] * L[k][j] for every owned row i >= k > j.
-        // Rows above the diagonal inside the diagonal slot pick up garbage that is never
-        // published, read or stored (same as the reference's unguarded register updates).
+        // Generic kernel: rows above the diagonal inside the diagonal slot pick up garbage that
+        // is never published, read or stored (like the reference's unguarded register updates).
 #pragma unroll
         for (int p = (j + 1) / 2; p < NP / 2; ++p) {
           const V2 v2 = *reinterpret_cast<const V2 *>(wbuf + p * PAIR);
@@ -139,7 +163,10 @@ potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const in
             if (k > j) {
               const T v = h ? v2.y : v2.x;
 #pragma unroll
-              for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
+              for (int s = k / G; s < S; ++s) {
+                if (!EXACT || s > k / G || l >= k % G)
+                  a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
+              }
             }
           }
         }
@@ -149,16 +176,17 @@ potrf_reg_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const in
       if (c == G - 1) {
 #pragma unroll
         for (int col = j - (G - 1); col <= j; ++col) {
-          T *pc = A + l + (long)col * lda;
 #pragma unroll
           for (int s = col / G; s < S; ++s) {
             const int row = G * s + l;
-            if (active && row >= col && row < n) stg_stream(pc + G * s, a[KX_IDX(s, col)]);
+            const bool keep = EXACT ? ((row | (SE - 1)) >= col) : (row >= col && row < n);
+            if (active && keep) stg_stream(pst + G * s, a[KX_IDX(s, col)]);
           }
+          pst += lda;
         }
       }
     }
-    if (info_mode && active && l == 0) info[mat] = bad;
+    if (!EXACT && info_mode && active && l == 0) info[mat] = bad;
     __syncwarp();  // the broadcast buffers are reused by the next warp-batch
 #undef KX_IDX
   }

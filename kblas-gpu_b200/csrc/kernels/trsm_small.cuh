@@ -37,59 +37,99 @@ enum TriOp { TRI_FORWARD = 0, TRI_BACKWARD = 1, TRI_BOTH = 2 };
 __device__ __forceinline__ void sched_fence() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); }
 
 // Stage the k x k lower factor of one matrix into shared memory: Ls[row + col*NP], padded
-// with the identity; invd[j] = 1 / L_jj.  One warp, coalesced column reads.
+// with the identity; invd[j] = 1 / L_jj.  One warp, coalesced column reads.  Two phases so that
+// all NP predicated loads are in flight before the first shared-memory store waits on one.
 template <typename T, int NP>
-__device__ __forceinline__ void stage_factor(const T *__restrict__ A, int lda, int k, T *__restrict__ Ls,
-                                             T *__restrict__ invd, int lane) {
+__device__ __forceinline__ void stage_factor_load(T (&v)[NP], const T *__restrict__ A, int lda, int k, int lane) {
   constexpr int SE = SectorElems<T>::value;
 #pragma unroll
   for (int col = 0; col < NP; ++col) {
-    T v = (lane == col) ? T(1) : T(0);
-    if (lane < NP) {
-      if (lane < k && col < k) {
-        v = T(0);
-        if ((lane | (SE - 1)) >= col) v = ldg_stream(A + lane + (long)col * lda);
-      }
-      Ls[lane + col * NP] = v;
-    }
-    if (lane == col) invd[col] = T(1) / v;
+    const bool inside = (lane < k) && (col < k);
+    v[col] = (!inside && lane == col) ? T(1) : T(0);
+    ldg_stream_if(v[col], A + lane + (long)col * lda, inside && ((lane | (SE - 1)) >= col));
+  }
+}
+template <typename T, int NP>
+__device__ __forceinline__ void stage_factor_store(const T (&v)[NP], T *__restrict__ Ls, T *__restrict__ invd, int lane) {
+#pragma unroll
+  for (int col = 0; col < NP; ++col) {
+    if (lane < NP) Ls[lane + col * NP] = v[col];
+    if (lane == col) invd[col] = T(1) / v[col];
   }
   __syncwarp();
+}
+template <typename T, int NP>
+__device__ __forceinline__ void stage_factor(const T *__restrict__ A, int lda, int k, T *__restrict__ Ls,
+                                             T *__restrict__ invd, int lane) {
+  T v[NP];
+  stage_factor_load<T, NP>(v, A, lda, k, lane);
+  stage_factor_store<T, NP>(v, Ls, invd, lane);
+}
+
+// Column j of the staged factor, rows > j, as NP/2 register pairs (pair p = rows 2p, 2p+1).
+// Issued one column AHEAD of its use (software pipeline): the FMAs of column j hide the
+// shared-memory latency of column j+1; the explicit double buffer gives ptxas the ILP that the
+// ordered (volatile) loads would otherwise deny it.
+template <typename T, int NP>
+__device__ __forceinline__ void load_factor_col(typename Vec2T<T>::type (&buf)[NP / 2], const T *Ls, int j) {
+#pragma unroll
+  for (int p = 0; p < NP / 2; ++p)
+    if (p >= (j + 1) / 2) buf[p] = lds_pair(Ls + 2 * p + j * NP);
 }
 
 // forward substitution on the NP-vector x (see file header)
 template <typename T, int NP>
 __device__ __forceinline__ void tri_forward(T (&x)[NP], const T *__restrict__ Ls, const T *__restrict__ invd) {
   typedef typename Vec2T<T>::type V2;
+  V2 cur[NP / 2], nxt[NP / 2];
+  load_factor_col<T, NP>(cur, Ls, 0);
+  T dinv = lds_one(invd);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     if (j % KX_TRI_FENCE == 0) sched_fence();
-    x[j] *= lds_one(invd + j);
+    T dnext = T(0);
+    if (j + 1 < NP) {
+      load_factor_col<T, NP>(nxt, Ls, j + 1);
+      dnext = lds_one(invd + j + 1);
+    }
+    x[j] *= dinv;
     const T nx = -x[j];
 #pragma unroll
     for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-      const V2 l2 = lds_pair(Ls + 2 * p + j * NP);
-      if (2 * p > j) x[2 * p] = fma_t(nx, l2.x, x[2 * p]);
-      x[2 * p + 1] = fma_t(nx, l2.y, x[2 * p + 1]);
+      if (2 * p > j) x[2 * p] = fma_t(nx, cur[p].x, x[2 * p]);
+      x[2 * p + 1] = fma_t(nx, cur[p].y, x[2 * p + 1]);
     }
+#pragma unroll
+    for (int p = 0; p < NP / 2; ++p) cur[p] = nxt[p];
+    dinv = dnext;
   }
 }
 
-// backward substitution on the NP-vector x (two partial sums shorten the FMA chain)
+// backward substitution on the NP-vector x (four partial sums shorten the FMA chain)
 template <typename T, int NP>
 __device__ __forceinline__ void tri_backward(T (&x)[NP], const T *__restrict__ Ls, const T *__restrict__ invd) {
   typedef typename Vec2T<T>::type V2;
+  V2 cur[NP / 2], nxt[NP / 2];
+  load_factor_col<T, NP>(cur, Ls, NP - 1);
+  T dinv = lds_one(invd + NP - 1);
 #pragma unroll
   for (int j = NP - 1; j >= 0; --j) {
     if (j % KX_TRI_FENCE == KX_TRI_FENCE - 1) sched_fence();
-    T acc0 = x[j], acc1 = T(0);
+    T dnext = T(0);
+    if (j > 0) {
+      load_factor_col<T, NP>(nxt, Ls, j - 1);
+      dnext = lds_one(invd + j - 1);
+    }
+    T acc[4] = {x[j], T(0), T(0), T(0)};
 #pragma unroll
     for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-      const V2 l2 = lds_pair(Ls + 2 * p + j * NP);
-      if (2 * p > j) acc0 = fma_t(-x[2 * p], l2.x, acc0);
-      acc1 = fma_t(-x[2 * p + 1], l2.y, acc1);
+      if (2 * p > j) acc[(2 * p) & 3] = fma_t(-x[2 * p], cur[p].x, acc[(2 * p) & 3]);
+      acc[(2 * p + 1) & 3] = fma_t(-x[2 * p + 1], cur[p].y, acc[(2 * p + 1) & 3]);
     }
-    x[j] = (acc0 + acc1) * lds_one(invd + j);
+    x[j] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * dinv;
+#pragma unroll
+    for (int p = 0; p < NP / 2; ++p) cur[p] = nxt[p];
+    dinv = dnext;
   }
 }
 
@@ -105,7 +145,7 @@ struct TriSmem {
 // k = order of the triangular factor (n for side R, m for side L); vec = the other dimension
 // of B (number of independent vectors).  OP selects forward / backward / both (potrs).
 template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED>
-__global__ void __launch_bounds__(WARPS * 32, LEFT ? 3 : 4)
+__global__ void __launch_bounds__(WARPS * 32, 3)
 tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                        BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,15 +163,23 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
 
   const T *__restrict__ A = Aref.at(mat);
   T *__restrict__ B = Bref.at(mat);
-  stage_factor<T, NP>(A, lda, k, Ls, invd, lane);
+  T fv[NP];
+  stage_factor_load<T, NP>(fv, A, lda, k, lane);  // NP loads in flight ...
 
   T x[NP];
   const int my = v0 + lane;  // my vector
   if (!LEFT) {
-    // vector = row `my` of B; element j at B[my + j*ldb]
+    // vector = row `my` of B; element j at B[my + j*ldb]   (... plus NP more, before anything waits)
 #pragma unroll
-    for (int j = 0; j < NP; ++j) x[j] = (my < vec && j < k) ? alpha * ldg_stream(B + my + (long)j * ldb) : T(0);
+    for (int j = 0; j < NP; ++j) {
+      x[j] = T(0);
+      ldg_stream_if(x[j], B + my + (long)j * ldb, my < vec && j < k);
+    }
+    stage_factor_store<T, NP>(fv, Ls, invd, lane);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) x[j] *= alpha;
   } else {
+    stage_factor_store<T, NP>(fv, Ls, invd, lane);
     // vector = column `my` of B; stage the k x 32 tile as tile[c*TS + i] (coalesced reads of B)
     for (int c = 0; c < 32; ++c) {
       const int colB = v0 + c;

@@ -11,23 +11,23 @@
 
 namespace kblasx {
 
-template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED>
+template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED, bool EXACT, bool LOCKSTEP>
 static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
                             int *info) {
   constexpr int MPW = 32 / G;
   const long per_cta = (long)WARPS * MPW;
-  // persistent warps: one wave of CTAs (MINB per SM), each warp strides over its warp-batches
+  auto kern = potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED, EXACT, LOCKSTEP>;
+  // persistent CTAs: one resident wave, each CTA strides over its share of the batch
   const long need = (batchCount + per_cta - 1) / per_cta;
   static int ctas_per_sm = 0;  // per instantiation
   if (ctas_per_sm == 0) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED>, WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, 0);
     ctas_per_sm = occ > 0 ? occ : MINB;
   }
   const long wave = (long)h->sm_count * ctas_per_sm;
   const long grid = need < wave ? need : wave;
-  potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED>
-      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
+  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -35,28 +35,36 @@ static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T,
 
 #define KX_STR2(x) #x
 #define KX_STR(x) KX_STR2(x)
-#define KX_LAUNCH_REG(NP, G, W, MB) \
-  launch_potrf_reg<T, NP, G, W, MB, STRIDED>(h, "potrf_reg<NP=" KX_STR(NP) ",G=" KX_STR(G) ",W=" KX_STR(W) ">", n, A, lda, batchCount, info)
+#define KX_LAUNCH_REG(NP, G, W, MB, EX, LS)                                                              \
+  launch_potrf_reg<T, NP, G, W, MB, STRIDED, EX, LS>(                                                    \
+      h, "potrf_reg<NP=" KX_STR(NP) ",G=" KX_STR(G) ",W=" KX_STR(W) ",MB=" KX_STR(MB) ",EX=" KX_STR(EX) ",LS=" KX_STR(LS) ">", \
+      n, A, lda, batchCount, info)
 
-// n <= 32: register-resident kernel, padded size NP = roundup(n, 8)
+// n <= 32: register-resident kernel, padded size NP = roundup(n, 8).  The EXACT instantiation
+// (n == NP, info untouched) carries no bounds predicates; everything else takes the generic one.
 template <typename T, bool STRIDED>
 static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
   const int v = h->variant_override;
-  if (n <= 8) return KX_LAUNCH_REG(8, 8, 4, 4);
-  if (n <= 16) return KX_LAUNCH_REG(16, 8, 4, 4);
-  if (n <= 24) return KX_LAUNCH_REG(24, 8, 4, 3);
-  if constexpr (sizeof(T) == 4) {
+  const bool exact = (n % 8 == 0) && (h->info_mode == KBLASX_INFO_COMPAT);
+  constexpr bool F32 = sizeof(T) == 4;
+  if (n <= 8) return exact ? KX_LAUNCH_REG(8, 8, 4, 4, true, false) : KX_LAUNCH_REG(8, 8, 4, 4, false, false);
+  if (n <= 16) return exact ? KX_LAUNCH_REG(16, 8, 4, 4, true, true) : KX_LAUNCH_REG(16, 8, 4, 4, false, true);
+  if (n <= 24) return exact ? KX_LAUNCH_REG(24, 8, 4, 3, true, true) : KX_LAUNCH_REG(24, 8, 4, 3, false, true);
+  if constexpr (F32) {
     // fp32: 80 values per lane fit a 128-register budget -> 16 resident warps per SM
+    if (!exact) return KX_LAUNCH_REG(32, 8, 4, 4, false, true);
     switch (v) {
-      case 1: return KX_LAUNCH_REG(32, 16, 4, 4);
-      case 2: return KX_LAUNCH_REG(32, 8, 4, 2);
-      default: return KX_LAUNCH_REG(32, 8, 4, 4);
+      case 1: return KX_LAUNCH_REG(32, 8, 4, 4, true, true);
+      case 3: return KX_LAUNCH_REG(32, 16, 4, 4, true, true);
+      default: return KX_LAUNCH_REG(32, 8, 8, 2, true, true);
     }
   } else {
+    // fp64: 160 registers of matrix data per lane -> one 8-warp CTA per SM, warps in lockstep
+    if (!exact) return KX_LAUNCH_REG(32, 8, 4, 2, false, true);
     switch (v) {
-      case 1: return KX_LAUNCH_REG(32, 16, 4, 3);
-      case 2: return KX_LAUNCH_REG(32, 8, 5, 2);
-      default: return KX_LAUNCH_REG(32, 8, 4, 2);
+      case 1: return KX_LAUNCH_REG(32, 8, 4, 2, true, true);
+      case 3: return KX_LAUNCH_REG(32, 16, 4, 3, true, true);
+      default: return KX_LAUNCH_REG(32, 8, 8, 1, true, true);
     }
   }
 }
