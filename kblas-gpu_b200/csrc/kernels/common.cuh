@@ -57,6 +57,15 @@ __device__ __forceinline__ void stg_stream(float *p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void stg_stream_if(double *p, double v, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.L1::no_allocate.f64 [%0], %1; }"
+               ::"l"(p), "d"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void stg_stream_if(float *p, float v, bool pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.L1::no_allocate.f32 [%0], %1; }"
+               ::"l"(p), "f"(v), "r"((int)pred) : "memory");
+}
+
 // ---- shared-memory pair loads -----------------------------------------------------------
 // asm volatile on purpose: the staged factor is immutable, and a plain (const __restrict__)
 // load lets the compiler keep every value it has ever read alive in registers across the

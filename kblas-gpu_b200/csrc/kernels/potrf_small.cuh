@@ -106,7 +106,8 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
           const bool inside = EXACT || ((row < n) && (col < n));
           const bool need = ((row | (SE - 1)) >= col);  // sector holds at least one lower element
           T v = (inside || row != col) ? T(0) : T(1);   // identity padding; 0 for skipped sectors
-          if (inside && need) v = ldg_stream(pc + G * s);
+          if (EXACT && s > col / G) v = ldg_stream(pc + G * s);      // always needed: plain load
+          else ldg_stream_if(v, pc + G * s, inside && need);         // predicated, branch-free
           a[KX_IDX(s, col)] = v;
         }
         pc += lda;
@@ -180,7 +181,7 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
           for (int s = col / G; s < S; ++s) {
             const int row = G * s + l;
             const bool keep = EXACT ? ((row | (SE - 1)) >= col) : (row >= col && row < n);
-            if (active && keep) stg_stream(pst + G * s, a[KX_IDX(s, col)]);
+            stg_stream_if(pst + G * s, a[KX_IDX(s, col)], active && keep);
           }
           pst += lda;
         }

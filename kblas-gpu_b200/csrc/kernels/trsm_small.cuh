@@ -181,9 +181,17 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
   } else {
     stage_factor_store<T, NP>(fv, Ls, invd, lane);
     // vector = column `my` of B; stage the k x 32 tile as tile[c*TS + i] (coalesced reads of B)
-    for (int c = 0; c < 32; ++c) {
-      const int colB = v0 + c;
-      if (lane < k && colB < vec) tile[c * TS + lane] = ldg_stream(B + lane + (long)colB * ldb);
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {  // 16 predicated loads in flight, then 16 stores
+      T tv[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        tv[c] = T(0);
+        ldg_stream_if(tv[c], B + lane + (long)(v0 + c0 + c) * ldb, lane < k && (v0 + c0 + c) < vec);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (lane < NP) tile[(c0 + c) * TS + lane] = tv[c];
     }
     __syncwarp();
 #pragma unroll
@@ -195,16 +203,17 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
 
   if (!LEFT) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j)
-      if (my < vec && j < k) stg_stream(B + my + (long)j * ldb, x[j]);
+    for (int j = 0; j < NP; ++j) stg_stream_if(B + my + (long)j * ldb, x[j], my < vec && j < k);
   } else {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < NP; ++j) tile[lane * TS + j] = x[j];
     __syncwarp();
+#pragma unroll 8
     for (int c = 0; c < 32; ++c) {
       const int colB = v0 + c;
-      if (lane < k && colB < vec) stg_stream(B + lane + (long)colB * ldb, tile[c * TS + lane]);
+      const T out = (lane < NP) ? tile[c * TS + lane] : T(0);  // lanes >= NP would read past the tile
+      stg_stream_if(B + lane + (long)colB * ldb, out, lane < k && colB < vec);
     }
   }
 }
