@@ -71,6 +71,11 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
   static_assert(NP % G == 0 && G % 2 == 0 && 32 % G == 0, "bad tiling");
 
   __shared__ __align__(16) T bc[WARPS * 2 * BUF_STRIDE];
+  // EXACT: original bits of the strict-upper elements that share a sector with the diagonal,
+  // NU per diagonal block and lane (element (row, c) with row < c <= row | (SE-1)), kept in shared
+  // memory from load to store so that the register updates need no predication
+  constexpr int NU = ((SE < G) ? SE : G) - 1;
+  __shared__ T sv[EXACT ? WARPS * S * NU * 32 : 1];
 
   const int n = EXACT ? NP : n_arg;
   const int info_mode = EXACT ? 0 : info_mode_arg;
@@ -114,6 +119,20 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
       }
     }
 
+    if (EXACT) {
+      // column of slot i for this lane: (l & ~(SE-1)) + 1 + i inside the diagonal block
+#pragma unroll
+      for (int t = 0; t < S; ++t)
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          T v = a[KX_IDX(t, G * t + 1 + i)];
+#pragma unroll
+          for (int h = SE; h < G; h += SE)
+            if (h + 1 + i < G) v = ((l & ~(SE - 1)) == h) ? a[KX_IDX(t, G * t + h + 1 + i)] : v;
+          sv[((warp * S + t) * NU + i) * 32 + lane] = v;
+        }
+    }
+
     // ---- pull the NEXT warp-batch of this warp into L2 while this one is being factored ----
     {
       const long nb = wb + (long)gridDim.x * WARPS;
@@ -137,9 +156,7 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
       }
       const T r = rsqrt_t(d);
 #pragma unroll
-      for (int s = t; s < S; ++s) {
-        if (!EXACT || s > t || l >= c) a[KX_IDX(s, j)] *= r;  // EXACT: keep the upper elements intact
-      }
+      for (int s = t; s < S; ++s) a[KX_IDX(s, j)] *= r;
 
       if (j + 1 < NP) {
         T *wbuf = wbase + (j & 1) * BUF_STRIDE;
@@ -153,8 +170,9 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
         }
         __syncwarp();
         // trailing update: A[i][k] -= L[i][j] * L[k][j] for every owned row i >= k > j.
-        // Generic kernel: rows above the diagonal inside the diagonal slot pick up garbage that
-        // is never published, read or stored (like the reference's unguarded register updates).
+        // Rows above the diagonal inside the diagonal slot pick up garbage that is never published
+        // or read (like the reference's unguarded register updates); the EXACT kernel stores the
+        // saved original bits for them, the generic one does not store them at all.
 #pragma unroll
         for (int p = (j + 1) / 2; p < NP / 2; ++p) {
           const V2 v2 = *reinterpret_cast<const V2 *>(wbuf + p * PAIR);
@@ -164,10 +182,7 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
             if (k > j) {
               const T v = h ? v2.y : v2.x;
 #pragma unroll
-              for (int s = k / G; s < S; ++s) {
-                if (!EXACT || s > k / G || l >= k % G)
-                  a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
-              }
+              for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
             }
           }
         }
@@ -181,7 +196,10 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
           for (int s = col / G; s < S; ++s) {
             const int row = G * s + l;
             const bool keep = EXACT ? ((row | (SE - 1)) >= col) : (row >= col && row < n);
-            stg_stream_if(pst + G * s, a[KX_IDX(s, col)], active && keep);
+            T val = a[KX_IDX(s, col)];
+            if (EXACT && s == col / G && (col % G) % SE != 0)  // sector straddles the diagonal
+              val = (l >= col % G) ? val : sv[((warp * S + s) * NU + ((col % G) % SE) - 1) * 32 + lane];
+            stg_stream_if(pst + G * s, val, active && keep);
           }
           pst += lda;
         }
