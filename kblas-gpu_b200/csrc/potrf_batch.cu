@@ -7,6 +7,7 @@
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
 #include "kernels/potrf_panel.cuh"
+#include "kernels/potrf_panel_dmma.cuh"
 #include "potrf_batch.h"
 
 namespace kblasx {
@@ -95,8 +96,32 @@ static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<
   return KBLAS_Success;
 }
 
+// fp64, n > 32: same panel algorithm with the update on the FP64 tensor path (kernels/potrf_panel_dmma.cuh)
+template <int THREADS, bool STRIDED>
+static int launch_potrf_panel_dmma(KBlasHandle *h, const char *name, int n, BatchRef<double, STRIDED> A, int lda,
+                                   int batchCount, int *info) {
+  auto kern = potrf_panel_dmma_kernel<THREADS, STRIDED>;
+  const size_t smem = PanelDmmaSmem<THREADS>::bytes;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
+    attr_set = true;
+  }
+  kern<<<(unsigned)batchCount, THREADS, smem, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
+  if constexpr (sizeof(T) == 8) {
+    if (h->variant_override != 9) {  // 9 = force the DFMA panel kernel (A/B comparisons)
+      if (n <= 64) return launch_potrf_panel_dmma<64, STRIDED>(h, "potrf_panel_dmma<T=64>", n, A, lda, batchCount, info);
+      if (n <= 128) return launch_potrf_panel_dmma<128, STRIDED>(h, "potrf_panel_dmma<T=128>", n, A, lda, batchCount, info);
+      return launch_potrf_panel_dmma<256, STRIDED>(h, "potrf_panel_dmma<T=256>", n, A, lda, batchCount, info);
+    }
+  }
   // THREADS*2 rows per slab: pick the smallest CTA that covers the first panel in one slab
   if (n <= 64) return launch_potrf_panel<T, 32, STRIDED>(h, "potrf_panel<T=32>", n, A, lda, batchCount, info);
   if (n <= 128) return launch_potrf_panel<T, 64, STRIDED>(h, "potrf_panel<T=64>", n, A, lda, batchCount, info);
