@@ -51,11 +51,17 @@ __device__ __forceinline__ void stage_factor_load(T (&v)[NP], const T *__restric
 }
 template <typename T, int NP>
 __device__ __forceinline__ void stage_factor_store(const T (&v)[NP], T *__restrict__ Ls, T *__restrict__ invd, int lane) {
+  // every load of the batch is issued before the first store can wait on one (ptxas otherwise
+  // interleaves LDG / STS to save registers and the in-order warp eats one memory latency per column)
+  sched_fence();
+  T dg = T(1);  // my own diagonal entry (select chain: ONE division per lane, all lanes at once;
+                // a per-column `if (lane == col) 1/v` serialises NP single-lane divisions)
 #pragma unroll
   for (int col = 0; col < NP; ++col) {
     if (lane < NP) Ls[lane + col * NP] = v[col];
-    if (lane == col) invd[col] = T(1) / v[col];
+    dg = (lane == col) ? v[col] : dg;
   }
+  if (lane < NP) invd[lane] = T(1) / dg;
   __syncwarp();
 }
 template <typename T, int NP>
@@ -164,22 +170,22 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
   const T *__restrict__ A = Aref.at(mat);
   T *__restrict__ B = Bref.at(mat);
   T fv[NP];
-  stage_factor_load<T, NP>(fv, A, lda, k, lane);  // NP loads in flight ...
+  stage_factor_load<T, NP>(fv, A, lda, k, lane);  // NP predicated loads in flight
+  stage_factor_store<T, NP>(fv, Ls, invd, lane);
 
   T x[NP];
   const int my = v0 + lane;  // my vector
   if (!LEFT) {
-    // vector = row `my` of B; element j at B[my + j*ldb]   (... plus NP more, before anything waits)
+    // vector = row `my` of B; element j at B[my + j*ldb]
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       x[j] = T(0);
       ldg_stream_if(x[j], B + my + (long)j * ldb, my < vec && j < k);
     }
-    stage_factor_store<T, NP>(fv, Ls, invd, lane);
+    sched_fence();
 #pragma unroll
     for (int j = 0; j < NP; ++j) x[j] *= alpha;
   } else {
-    stage_factor_store<T, NP>(fv, Ls, invd, lane);
     // vector = column `my` of B; stage the k x 32 tile as tile[c*TS + i] (coalesced reads of B)
 #pragma unroll
     for (int c0 = 0; c0 < 32; c0 += 16) {  // 16 predicated loads in flight, then 16 stores
@@ -189,6 +195,7 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
         tv[c] = T(0);
         ldg_stream_if(tv[c], B + lane + (long)(v0 + c0 + c) * ldb, lane < k && (v0 + c0 + c) < vec);
       }
+      sched_fence();
 #pragma unroll
       for (int c = 0; c < 16; ++c)
         if (lane < NP) tile[(c0 + c) * TS + lane] = tv[c];
@@ -216,6 +223,59 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
       stg_stream_if(B + lane + (long)colB * ldb, out, lane < k && colB < vec);
     }
   }
+}
+
+// ---- packed variant: vec <= 16 right-hand-side vectors per matrix -> several matrices per warp ------
+// A group of GP (8 or 16) lanes owns one matrix; lane lg of the group owns vector lg.  Each group has
+// its own staged factor, so the substitution's shared-memory reads are 32/GP-address broadcasts.
+// (With one matrix per warp an 8 x 8 problem kept 24 of 32 lanes idle: 0.15 of the HBM roofline,
+// slower than the reference's 8-lane register kernels, Xtrsm_batch_kernels.cuh:36-133.)
+template <typename T, int NP, int GP, bool LEFT, int OP, int WARPS, bool STRIDED>
+__global__ void __launch_bounds__(WARPS * 32)
+tri_solve_packed_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
+                        BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount) {
+  constexpr int MPW = 32 / GP;                 // matrices per warp
+  constexpr int FSZ = NP * NP + NP;            // staged factor + reciprocal diagonal
+  __shared__ __align__(16) T smem[WARPS * MPW * FSZ];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = lane / GP, lg = lane % GP;
+  T *Lw = smem + warp * MPW * FSZ;
+
+  const long wtask = (long)blockIdx.x * WARPS + warp;  // warp-batch of MPW matrices
+  const long mat0 = wtask * MPW;
+  if (mat0 >= (long)batchCount) return;  // warp-uniform
+
+  // ---- stage the MPW factors: the whole warp loads one factor at a time (lane = row) -------------
+#pragma unroll
+  for (int q = 0; q < MPW; ++q) {
+    const long mq = (mat0 + q < (long)batchCount) ? mat0 + q : (long)batchCount - 1;
+    T fv[NP];
+    stage_factor_load<T, NP>(fv, Aref.at(mq), lda, k, lane);
+    stage_factor_store<T, NP>(fv, Lw + q * FSZ, Lw + q * FSZ + NP * NP, lane);
+  }
+  const long mat = mat0 + g;
+  const bool have = (mat < (long)batchCount) && (lg < vec);
+  T *__restrict__ B = Bref.at(mat < (long)batchCount ? mat : (long)batchCount - 1);
+  const T *Ls = Lw + g * FSZ;
+  const T *invd = Ls + NP * NP;
+
+  // element j of my vector: side R: B[lg + j*ldb] (row lg), side L: B[j + lg*ldb] (column lg)
+  T x[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    x[j] = T(0);
+    ldg_stream_if(x[j], B + (LEFT ? ((long)j + (long)lg * ldb) : ((long)lg + (long)j * ldb)), have && j < k);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) x[j] *= alpha;
+
+  if (OP == TRI_FORWARD || OP == TRI_BOTH) tri_forward<T, NP>(x, Ls, invd);
+  if (OP == TRI_BACKWARD || OP == TRI_BOTH) tri_backward<T, NP>(x, Ls, invd);
+
+#pragma unroll
+  for (int j = 0; j < NP; ++j)
+    stg_stream_if(B + (LEFT ? ((long)j + (long)lg * ldb) : ((long)lg + (long)j * ldb)), x[j], have && j < k);
 }
 
 }  // namespace kblasx

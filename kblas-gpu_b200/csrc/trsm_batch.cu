@@ -32,6 +32,20 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
   return KBLAS_Success;
 }
 
+// vec <= 16: several matrices per warp (kernels/trsm_small.cuh, packed variant)
+template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_packed(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                             int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;
+  const long wtasks = ((long)batchCount + MPW - 1) / MPW;
+  const long grid = (wtasks + WARPS - 1) / WARPS;
+  tri_solve_packed_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 // k > 32: blocked substitution, one warp per (matrix, 32-vector slab) (kernels/trsm_blocked.cuh)
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
@@ -50,6 +64,11 @@ static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  // few right-hand sides and a small factor: pack 4 / 2 matrices per warp
+  if (k <= 8 && vec <= 8) return launch_tri_packed<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 8 && vec <= 16) return launch_tri_packed<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 16 && vec <= 16) return launch_tri_packed<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 24) return launch_tri_small<T, 24, LEFT, OP, STRIDED>(h, "tri_small<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);

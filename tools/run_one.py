@@ -7,7 +7,8 @@ import bench
 kb = importlib.import_module("kblas-gpu_b200")
 op, n = sys.argv[1], int(sys.argv[2])
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 18
-dt, m = torch.float64, (16 if op.endswith("ptr") else n)
+dt = torch.float32 if os.environ.get("F32") else torch.float64
+m = (16 if op.endswith("ptr") else n)
 P = bench.make_spd(torch, batch, n, dt, 1)
 B = torch.rand((batch, n, m), device="cuda", dtype=dt)
 h = kb.Handle()
