@@ -25,6 +25,24 @@ __device__ __forceinline__ long b_index(int v, int e, int ldb) {
   return LEFT ? ((long)e + (long)v * ldb) : ((long)v + (long)e * ldb);
 }
 
+// Stage a 32 x 32 tile of the factor in MEMORY order: Ts[i*NB + lane] = A[(r0 + lane) + (c0 + i)*lda]
+// (zero outside nr x nc).  32 predicated loads in flight, then 32 conflict-free stores.
+template <typename T>
+__device__ __forceinline__ void stage_tile(T *Ts, const T *__restrict__ A, int lda, int r0, int c0, int nr, int nc,
+                                           int lane) {
+  constexpr int NB = 32;
+  T v[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    v[i] = T(0);
+    ldg_stream_if(v[i], A + (r0 + lane) + (long)(c0 + i) * lda, lane < nr && i < nc);
+  }
+  sched_fence();
+#pragma unroll
+  for (int i = 0; i < NB; ++i) Ts[i * NB + lane] = v[i];
+  __syncwarp();
+}
+
 template <typename T, bool LEFT, bool FORWARD>
 __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, const T *__restrict__ A, const int lda,
                                                  T *__restrict__ B, const int ldb, const int my, const bool have,
@@ -38,32 +56,53 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
     const int jb = (k - j0 < NB) ? (k - j0) : NB;
     T x[NB];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) x[c] = (have && c < jb) ? alpha * B[b_index<LEFT>(my, j0 + c, ldb)] : T(0);
+    for (int c = 0; c < NB; ++c) {
+      x[c] = T(0);
+      ldg_stream_if(x[c], B + b_index<LEFT>(my, j0 + c, ldb), have && c < jb);
+    }
+    sched_fence();
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] *= alpha;
 
     // ---- contributions of the blocks already solved -------------------------------------------
     for (int bk = 0; bk < bi; ++bk) {
       const int K = FORWARD ? bk : (nblk - 1 - bk);
       const int k0 = K * NB;
       const int kb = (k - k0 < NB) ? (k - k0) : NB;
-      __syncwarp();
-      // S[kk*NB + c] = coefficient of x_K[kk] in equation c of block J:
-      //   forward: L[j0 + c][k0 + kk]     backward: L[k0 + kk][j0 + c]
-      for (int e = lane; e < NB * NB; e += 32) {
-        int c, kk;
-        long src;
-        if (FORWARD) { c = e % NB; kk = e / NB; src = (long)(j0 + c) + (long)(k0 + kk) * lda; }
-        else         { kk = e % NB; c = e / NB; src = (long)(k0 + kk) + (long)(j0 + c) * lda; }
-        S[kk * NB + c] = (c < jb && kk < kb) ? A[src] : T(0);
-      }
-      __syncwarp();
-#pragma unroll 4
-      for (int kk = 0; kk < NB; ++kk) {
-        const T nx = (have && kk < kb) ? -B[b_index<LEFT>(my, k0 + kk, ldb)] : T(0);
+      // my already solved entries of block K (negated)
+      T nx[NB];
 #pragma unroll
-        for (int c = 0; c < NB; c += 2) {
-          const V2 s2 = lds_pair(S + kk * NB + c);
-          x[c] = fma_t(nx, s2.x, x[c]);
-          x[c + 1] = fma_t(nx, s2.y, x[c + 1]);
+      for (int kk = 0; kk < NB; ++kk) {
+        nx[kk] = T(0);
+        ldg_stream_if(nx[kk], B + b_index<LEFT>(my, k0 + kk, ldb), have && kk < kb);
+      }
+      __syncwarp();  // previous users of S are done
+      if (FORWARD) {
+        // coefficient of x_K[kk] in equation c: L[j0 + c][k0 + kk] = Ts[kk*NB + c]  (axpy form)
+        stage_tile<T>(S, A, lda, j0, k0, jb, kb, lane);
+#pragma unroll 8
+        for (int kk = 0; kk < NB; ++kk) {
+          const T m1 = -nx[kk];
+#pragma unroll
+          for (int c = 0; c < NB; c += 2) {
+            const V2 s2 = lds_pair(S + kk * NB + c);
+            x[c] = fma_t(m1, s2.x, x[c]);
+            x[c + 1] = fma_t(m1, s2.y, x[c + 1]);
+          }
+        }
+      } else {
+        // coefficient of x_K[kk] in equation c: L[k0 + kk][j0 + c] = Ts[c*NB + kk]  (dot form)
+        stage_tile<T>(S, A, lda, k0, j0, kb, jb, lane);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+          for (int kk = 0; kk < NB; kk += 2) {
+            const V2 s2 = lds_pair(S + c * NB + kk);
+            acc[kk & 3] = fma_t(nx[kk], s2.x, acc[kk & 3]);
+            acc[(kk + 1) & 3] = fma_t(nx[kk + 1], s2.y, acc[(kk + 1) & 3]);
+          }
+          x[c] -= (acc[0] + acc[1]) + (acc[2] + acc[3]);
         }
       }
     }
@@ -74,8 +113,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
     if (FORWARD) tri_forward<T, NB>(x, Lkk, invd);
     else tri_backward<T, NB>(x, Lkk, invd);
 #pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (have && c < jb) B[b_index<LEFT>(my, j0 + c, ldb)] = x[c];
+    for (int c = 0; c < NB; ++c) stg_stream_if(B + b_index<LEFT>(my, j0 + c, ldb), x[c], have && c < jb);
   }
 }
 
