@@ -24,12 +24,11 @@
 
 namespace kblasx {
 
-template <typename T, int THREADS, bool STRIDED>
+template <typename T, int THREADS, int R, bool STRIDED>
 __global__ void __launch_bounds__(THREADS)
 potrf_panel_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
                    const int info_mode) {
-  constexpr int NB = 32;             // panel width
-  constexpr int R = 2;               // rows per thread
+  constexpr int NB = 32;             // panel width; R = rows per thread
   constexpr int SLAB = THREADS * R;  // rows per slab
   typedef typename Vec2T<T>::type V2;
 
@@ -56,32 +55,53 @@ potrf_panel_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const 
         valid[q] = row[q] < n;
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-          T v = T(0);
-          if (valid[q] && c < jb) v = ldg_stream(A + row[q] + (long)(j0 + c) * lda);
-          p[q][c] = v;
+          p[q][c] = T(0);
+          ldg_stream_if(p[q][c], A + row[q] + (long)(j0 + c) * lda, valid[q] && c < jb);  // branch-free
         }
       }
 
       // ---- 2. left-looking update with every previously factored block column ---------------
       for (int k0 = 0; k0 < j0; k0 += NB) {
         __syncthreads();  // S is about to be overwritten
-        for (int e = tid; e < NB * NB; e += THREADS) {
-          const int c = e % NB, kk = e / NB;
-          S[kk * NB + c] = (c < jb) ? A[(j0 + c) + (long)(k0 + kk) * lda] : T(0);
+        {
+          // all loads of the tile in flight, then the (conflict-free) stores
+          constexpr int PER = NB * NB / THREADS;
+          T tv[PER];
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int e = tid + i * THREADS, c = e % NB, kk = e / NB;
+            tv[i] = T(0);
+            ldg_stream_if(tv[i], A + (j0 + c) + (long)(k0 + kk) * lda, c < jb);
+          }
+          sched_fence();
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int e = tid + i * THREADS;
+            S[(e / NB) * NB + (e % NB)] = tv[i];
+          }
         }
         __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < NB; ++kk) {
-          T na[R];
 #pragma unroll
-          for (int q = 0; q < R; ++q) na[q] = valid[q] ? -A[row[q] + (long)(k0 + kk) * lda] : T(0);
+        for (int kc = 0; kc < NB; kc += 8) {
+          // my rows' entries of 8 already factored columns at a time (loads batched ahead of the FMAs)
+          T na[R][8];
 #pragma unroll
-          for (int c = 0; c < NB; c += 2) {
-            const V2 s2 = lds_pair(S + kk * NB + c);
+          for (int q = 0; q < R; ++q)
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-              p[q][c] = fma_t(na[q], s2.x, p[q][c]);
-              p[q][c + 1] = fma_t(na[q], s2.y, p[q][c + 1]);
+            for (int i = 0; i < 8; ++i) {
+              na[q][i] = T(0);
+              ldg_stream_if(na[q][i], A + row[q] + (long)(k0 + kc + i) * lda, valid[q]);
+            }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int c = 0; c < NB; c += 2) {
+              const V2 s2 = lds_pair(S + (kc + i) * NB + c);
+#pragma unroll
+              for (int q = 0; q < R; ++q) {
+                p[q][c] = fma_t(-na[q][i], s2.x, p[q][c]);
+                p[q][c + 1] = fma_t(-na[q][i], s2.y, p[q][c + 1]);
+              }
             }
           }
         }
@@ -126,7 +146,7 @@ potrf_panel_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const 
       for (int q = 0; q < R; ++q) {
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-          if (valid[q] && c < jb && row[q] >= j0 + c) stg_stream(A + row[q] + (long)(j0 + c) * lda, p[q][c]);
+          stg_stream_if(A + row[q] + (long)(j0 + c) * lda, p[q][c], valid[q] && c < jb && row[q] >= j0 + c);
         }
       }
       // rows of later slabs reuse Lkk; the next panel's S / Lkk writes are fenced by the

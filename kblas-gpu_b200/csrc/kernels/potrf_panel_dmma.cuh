@@ -82,7 +82,7 @@ potrf_panel_dmma_kernel(const int n, BatchRef<double, STRIDED> Aref, const int l
           brow[b] = brow[b] < n ? brow[b] : n - 1;
         }
         const T *col = A + (long)fk * lda;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < j0; k += 4) {
           T af[4], bf[4];
 #pragma unroll

@@ -86,10 +86,10 @@ static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
 }
 
 // n > 32: one CTA per matrix, left-looking 32-column panels (kernels/potrf_panel.cuh)
-template <typename T, int THREADS, bool STRIDED>
+template <typename T, int THREADS, int R, bool STRIDED>
 static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
                               int *info) {
-  potrf_panel_kernel<T, THREADS, STRIDED><<<(unsigned)batchCount, THREADS, 0, h->stream>>>(n, A, lda, batchCount, info,
+  potrf_panel_kernel<T, THREADS, R, STRIDED><<<(unsigned)batchCount, THREADS, 0, h->stream>>>(n, A, lda, batchCount, info,
                                                                                             h->info_mode);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
@@ -116,16 +116,31 @@ static int launch_potrf_panel_dmma(KBlasHandle *h, const char *name, int n, Batc
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
   if constexpr (sizeof(T) == 8) {
-    if (h->variant_override != 9) {  // 9 = force the DFMA panel kernel (A/B comparisons)
-      if (n <= 64) return launch_potrf_panel_dmma<64, STRIDED>(h, "potrf_panel_dmma<T=64>", n, A, lda, batchCount, info);
-      if (n <= 128) return launch_potrf_panel_dmma<128, STRIDED>(h, "potrf_panel_dmma<T=128>", n, A, lda, batchCount, info);
+    const int v = h->variant_override;
+    if (v != 9) {  // 9 = force the DFMA panel kernel (A/B comparisons)
+      // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
+      // pivot chain of the diagonal blocks (11..14 = tuning overrides)
+      // measured (B200, batch 64K, n = 64 / 128 / 256): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
+      // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6
+      int threads = 32;
+      if (v >= 11 && v <= 14) threads = 32 << (v - 11);
+      if (threads == 32) return launch_potrf_panel_dmma<32, STRIDED>(h, "potrf_panel_dmma<T=32>", n, A, lda, batchCount, info);
+      if (threads == 64) return launch_potrf_panel_dmma<64, STRIDED>(h, "potrf_panel_dmma<T=64>", n, A, lda, batchCount, info);
+      if (threads == 128) return launch_potrf_panel_dmma<128, STRIDED>(h, "potrf_panel_dmma<T=128>", n, A, lda, batchCount, info);
       return launch_potrf_panel_dmma<256, STRIDED>(h, "potrf_panel_dmma<T=256>", n, A, lda, batchCount, info);
     }
   }
-  // THREADS*2 rows per slab: pick the smallest CTA that covers the first panel in one slab
-  if (n <= 64) return launch_potrf_panel<T, 32, STRIDED>(h, "potrf_panel<T=32>", n, A, lda, batchCount, info);
-  if (n <= 128) return launch_potrf_panel<T, 64, STRIDED>(h, "potrf_panel<T=64>", n, A, lda, batchCount, info);
-  return launch_potrf_panel<T, 128, STRIDED>(h, "potrf_panel<T=128>", n, A, lda, batchCount, info);
+  // THREADS*2 rows per slab
+  int threads = 32;  // one warp per matrix (measured best for n = 64 / 128 / 256, like the fp64 kernel)
+  const int v = h->variant_override;
+  if (v >= 11 && v <= 13) threads = 32 << (v - 11);
+  if constexpr (sizeof(T) == 4) {
+    if (v == 15) return launch_potrf_panel<T, 32, 4, STRIDED>(h, "potrf_panel<T=32,R=4>", n, A, lda, batchCount, info);
+    if (v == 16) return launch_potrf_panel<T, 64, 4, STRIDED>(h, "potrf_panel<T=64,R=4>", n, A, lda, batchCount, info);
+  }
+  if (threads == 32) return launch_potrf_panel<T, 32, 2, STRIDED>(h, "potrf_panel<T=32,R=2>", n, A, lda, batchCount, info);
+  if (threads == 64) return launch_potrf_panel<T, 64, 2, STRIDED>(h, "potrf_panel<T=64,R=2>", n, A, lda, batchCount, info);
+  return launch_potrf_panel<T, 128, 2, STRIDED>(h, "potrf_panel<T=128,R=2>", n, A, lda, batchCount, info);
 }
 
 // Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)
