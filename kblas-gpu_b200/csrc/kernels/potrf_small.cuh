@@ -58,7 +58,7 @@ __device__ __forceinline__ void prefetch_lower_l2(const T *A, int n, int lda, in
 template <typename T, int NP, int G, int WARPS, int MINB, bool STRIDED, bool EXACT, bool LOCKSTEP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount,
-                 int *__restrict__ info, const int info_mode_arg) {
+                 int *__restrict__ info, const int info_mode_arg, const unsigned stagger_ns) {
   constexpr int S = NP / G;                    // row slots per lane
   constexpr int MPW = 32 / G;                  // matrices per warp
   constexpr int GH = (16 / G) > 0 ? (16 / G) : 1;  // lane groups per half-warp
@@ -89,6 +89,9 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
   // covers matrices [wb*MPW, wb*MPW + MPW)
   const long nwb = ((long)batchCount + MPW - 1) / MPW;
   const long ncb = (nwb + WARPS - 1) / WARPS;
+  // MINB >= 2 lockstep CTAs per SM: start the second half of the grid half a warp-batch late so that
+  // one CTA's load burst overlaps the other's arithmetic (CTAs b and b + #SM share an SM)
+  if (LOCKSTEP && MINB >= 2 && stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep(stagger_ns);
   for (long cb = blockIdx.x; cb < ncb; cb += gridDim.x) {
     if (LOCKSTEP) __syncthreads();
     const long wb = cb * WARPS + warp;

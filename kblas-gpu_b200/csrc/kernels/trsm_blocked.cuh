@@ -43,12 +43,19 @@ __device__ __forceinline__ void stage_tile(T *Ts, const T *__restrict__ A, int l
   __syncwarp();
 }
 
-template <typename T, bool LEFT, bool FORWARD>
-__device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, const T *__restrict__ A, const int lda,
+// GP = lanes per matrix: 32 (one matrix per warp, vec may span several 32-vector slabs) or 16 / 8
+// (vec <= GP right-hand sides: 2 / 4 matrices per warp, each lane group with its own staged tiles --
+// posv with 16 right-hand-side rows otherwise leaves half of every warp idle).
+template <typename T, bool LEFT, bool FORWARD, int GP>
+__device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, const T *const (&Aq)[32 / GP], const int lda,
                                                  T *__restrict__ B, const int ldb, const int my, const bool have,
-                                                 T *Lkk, T *invd, T *S, const int lane) {
+                                                 T *Lkk_all, T *S_all, const int lane) {
   constexpr int NB = 32;
+  constexpr int MPW = 32 / GP;
+  constexpr int FSZ = NB * NB + NB;
   typedef typename Vec2T<T>::type V2;
+  const int g = lane / GP;
+  T *Lkk = Lkk_all + g * FSZ, *invd = Lkk + NB * NB, *S = S_all + g * NB * NB;
   const int nblk = (k + NB - 1) / NB;
   for (int bi = 0; bi < nblk; ++bi) {
     const int J = FORWARD ? bi : (nblk - 1 - bi);
@@ -69,7 +76,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       const int K = FORWARD ? bk : (nblk - 1 - bk);
       const int k0 = K * NB;
       const int kb = (k - k0 < NB) ? (k - k0) : NB;
-      // my already solved entries of block K (negated)
+      // my already solved entries of block K
       T nx[NB];
 #pragma unroll
       for (int kk = 0; kk < NB; ++kk) {
@@ -79,7 +86,8 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       __syncwarp();  // previous users of S are done
       if (FORWARD) {
         // coefficient of x_K[kk] in equation c: L[j0 + c][k0 + kk] = Ts[kk*NB + c]  (axpy form)
-        stage_tile<T>(S, A, lda, j0, k0, jb, kb, lane);
+#pragma unroll
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * NB * NB, Aq[q], lda, j0, k0, jb, kb, lane);
 #pragma unroll 8
         for (int kk = 0; kk < NB; ++kk) {
           const T m1 = -nx[kk];
@@ -92,7 +100,8 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
         }
       } else {
         // coefficient of x_K[kk] in equation c: L[k0 + kk][j0 + c] = Ts[c*NB + kk]  (dot form)
-        stage_tile<T>(S, A, lda, k0, j0, kb, jb, lane);
+#pragma unroll
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * NB * NB, Aq[q], lda, k0, j0, kb, jb, lane);
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
           T acc[4] = {T(0), T(0), T(0), T(0)};
@@ -109,7 +118,9 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
 
     // ---- solve against the diagonal block ------------------------------------------------------
     __syncwarp();
-    stage_factor<T, NB>(A + j0 + (long)j0 * lda, lda, jb, Lkk, invd, lane);
+#pragma unroll
+    for (int q = 0; q < MPW; ++q)
+      stage_factor<T, NB>(Aq[q] + j0 + (long)j0 * lda, lda, jb, Lkk_all + q * FSZ, Lkk_all + q * FSZ + NB * NB, lane);
     if (FORWARD) tri_forward<T, NB>(x, Lkk, invd);
     else tri_backward<T, NB>(x, Lkk, invd);
 #pragma unroll
@@ -117,31 +128,44 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
   }
 }
 
+template <typename T, int GP>
+struct TriBlockedSmem {
+  static constexpr int NB = 32;
+  static constexpr int per_warp = (32 / GP) * (2 * NB * NB + NB);  // elements of T
+};
+
 // OP: TRI_FORWARD / TRI_BACKWARD / TRI_BOTH (forward with alpha, then backward with 1)
-template <typename T, bool LEFT, int OP, int WARPS, bool STRIDED>
+template <typename T, bool LEFT, int OP, int GP, int WARPS, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32)
 tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                          BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
   constexpr int NB = 32;
-  __shared__ __align__(16) T smem[WARPS * (2 * NB * NB + NB)];
+  constexpr int MPW = 32 / GP;
+  constexpr int FSZ = NB * NB + NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  T *Lkk = smem + warp * (2 * NB * NB + NB);
-  T *S = Lkk + NB * NB;
-  T *invd = S + NB * NB;
+  T *Lkk_all = reinterpret_cast<T *>(smem_raw) + warp * TriBlockedSmem<T, GP>::per_warp;
+  T *S_all = Lkk_all + MPW * FSZ;
 
+  // task = (warp-batch of MPW matrices, slab); slabs == 1 when packed
   const long task = (long)blockIdx.x * WARPS + warp;
-  if (task >= (long)batchCount * slabs) return;  // warp-uniform
-  const long mat = task / slabs;
-  const int my = (int)(task % slabs) * 32 + lane;
-  const bool have = my < vec;
-  const T *__restrict__ A = Aref.at(mat);
-  T *__restrict__ B = Bref.at(mat);
+  const long wbatches = ((long)batchCount + MPW - 1) / MPW;
+  if (task >= wbatches * slabs) return;  // warp-uniform
+  const long mat0 = (task / slabs) * MPW;
+  const int g = lane / GP;
+  const int my = (int)(task % slabs) * 32 + (lane % GP);
+  const long last = (long)batchCount - 1;
+  const T *Aq[MPW];
+#pragma unroll
+  for (int q = 0; q < MPW; ++q) Aq[q] = Aref.at(mat0 + q < last ? mat0 + q : last);
+  const bool have = (mat0 + g <= last) && (my < vec);
+  T *__restrict__ B = Bref.at(mat0 + g < last ? mat0 + g : last);
 
   if (OP == TRI_FORWARD || OP == TRI_BOTH)
-    tri_blocked_pass<T, LEFT, true>(k, alpha, A, lda, B, ldb, my, have, Lkk, invd, S, lane);
+    tri_blocked_pass<T, LEFT, true, GP>(k, alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane);
   if (OP == TRI_BACKWARD || OP == TRI_BOTH)
-    tri_blocked_pass<T, LEFT, false>(k, OP == TRI_BOTH ? T(1) : alpha, A, lda, B, ldb, my, have, Lkk, invd, S, lane);
+    tri_blocked_pass<T, LEFT, false, GP>(k, OP == TRI_BOTH ? T(1) : alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane);
 }
 
 }  // namespace kblasx

@@ -3,6 +3,7 @@
 // Counterpart of reference src/batch_triangular/Xpotrf_batch.cu:44-160 (entry points,
 // workspace check) and Xpotrf_batch_drivers.cuh:30-137 (driver).  The reference's driver
 // recursion (n/2 split -> potrf, trsm, syrk, potrf launches) is gone: one kernel per call.
+#include <cstdlib>
 #include "kblas.h"
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
@@ -28,7 +29,12 @@ static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T,
   }
   const long wave = (long)h->sm_count * ctas_per_sm;
   const long grid = need < wave ? need : wave;
-  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
+  static int stagger = -1;  // ns; env KBLAS_B200_STAGGER_NS (tuning)
+  if (stagger < 0) {
+    const char *e = getenv("KBLAS_B200_STAGGER_NS");
+    stagger = e ? atoi(e) : 0;
+  }
+  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode, (unsigned)stagger);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;

@@ -46,19 +46,38 @@ static int launch_tri_packed(KBlasHandle *h, const char *name, int k, int vec, T
   return KBLAS_Success;
 }
 
-// k > 32: blocked substitution, one warp per (matrix, 32-vector slab) (kernels/trsm_blocked.cuh)
+// k > 32: blocked substitution, one warp per (matrix, 32-vector slab), or 2 / 4 matrices per warp when
+// there are at most 16 / 8 right-hand-side vectors (kernels/trsm_blocked.cuh)
+template <typename T, bool LEFT, int OP, int GP, bool STRIDED>
+static int launch_tri_blocked_gp(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                                 int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int MPW = 32 / GP;
+  constexpr size_t per_warp = TriBlockedSmem<T, GP>::per_warp * sizeof(T);
+  constexpr int WARPS = (per_warp * 4 <= 70000) ? 4 : (per_warp * 2 <= 70000) ? 2 : 1;
+  const int slabs = (GP == 32) ? (vec + 31) / 32 : 1;
+  const long tasks = (((long)batchCount + MPW - 1) / MPW) * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  auto kern = tri_solve_blocked_kernel<T, LEFT, OP, GP, WARPS, STRIDED>;
+  const size_t smem = per_warp * WARPS;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
+    attr_set = true;
+  }
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                               BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  constexpr int WARPS = sizeof(T) == 8 ? 2 : 4;  // 16.5 KB (fp64) / 8.3 KB (fp32) of shared memory per warp
-  const int slabs = (vec + 31) / 32;
-  const long tasks = (long)batchCount * slabs;
-  const long grid = (tasks + WARPS - 1) / WARPS;
-  tri_solve_blocked_kernel<T, LEFT, OP, WARPS, STRIDED>
-      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
-  h->note_launch("tri_blocked");
-  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
-  return KBLAS_Success;
+  if (vec <= 8 && h->variant_override != 9)
+    return launch_tri_blocked_gp<T, LEFT, OP, 8, STRIDED>(h, "tri_blocked<GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (vec <= 16 && h->variant_override != 9)
+    return launch_tri_blocked_gp<T, LEFT, OP, 16, STRIDED>(h, "tri_blocked<GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  return launch_tri_blocked_gp<T, LEFT, OP, 32, STRIDED>(h, "tri_blocked<GP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
 }
 
 template <typename T, bool LEFT, int OP, bool STRIDED>
