@@ -246,36 +246,70 @@ tri_solve_packed_kernel(const int k, const int vec, const T alpha, BatchRef<cons
   const long mat0 = wtask * MPW;
   if (mat0 >= (long)batchCount) return;  // warp-uniform
 
-  // ---- stage the MPW factors: the whole warp loads one factor at a time (lane = row) -------------
+  // ---- all global loads of this warp-batch are issued before anything waits: the MPW factors (the
+  //      whole warp loads one factor at a time, lane = row) and, below, my row of B ---------------------
+  T fv[MPW][NP];
 #pragma unroll
   for (int q = 0; q < MPW; ++q) {
     const long mq = (mat0 + q < (long)batchCount) ? mat0 + q : (long)batchCount - 1;
-    T fv[NP];
-    stage_factor_load<T, NP>(fv, Aref.at(mq), lda, k, lane);
-    stage_factor_store<T, NP>(fv, Lw + q * FSZ, Lw + q * FSZ + NP * NP, lane);
+    stage_factor_load<T, NP>(fv[q], Aref.at(mq), lda, k, lane);
   }
   const long mat = mat0 + g;
-  const bool have = (mat < (long)batchCount) && (lg < vec);
   T *__restrict__ B = Bref.at(mat < (long)batchCount ? mat : (long)batchCount - 1);
   const T *Ls = Lw + g * FSZ;
   const T *invd = Ls + NP * NP;
 
-  // element j of my vector: side R: B[lg + j*ldb] (row lg), side L: B[j + lg*ldb] (column lg)
+  // Coalesced access for both sides: lane lg of a group reads ROW lg of B, one column per instruction
+  // (GP consecutive elements = one contiguous segment per matrix).  Side R: that row is my vector.
+  // Side L: my vector is COLUMN lg, so the rows are transposed through a padded shared-memory tile
+  // (stride NP+1: conflict-free both ways) instead of per-lane strided global accesses.
+  __shared__ T tiles[LEFT ? WARPS * MPW * GP * (NP + 1) : 1];
+  T *tile = tiles + (LEFT ? (warp * MPW + g) * GP * (NP + 1) : 0);
+  const int nrow = LEFT ? k : vec;   // rows of B
+  const int ncol = LEFT ? vec : k;   // columns of B
+  const bool hrow = (mat < (long)batchCount) && (lg < nrow);
+  constexpr int NC = LEFT ? GP : NP; // columns held per lane while loading
   T x[NP];
+  {
+    T t[NC];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    x[j] = T(0);
-    ldg_stream_if(x[j], B + (LEFT ? ((long)j + (long)lg * ldb) : ((long)lg + (long)j * ldb)), have && j < k);
+    for (int c = 0; c < NC; ++c) {
+      t[c] = T(0);
+      ldg_stream_if(t[c], B + (long)lg + (long)c * ldb, hrow && c < ncol);
+    }
+#pragma unroll
+    for (int q = 0; q < MPW; ++q) stage_factor_store<T, NP>(fv[q], Lw + q * FSZ, Lw + q * FSZ + NP * NP, lane);  // fences first
+    if (!LEFT) {
+#pragma unroll
+      for (int j = 0; j < NP; ++j) x[j] = alpha * t[j < NC ? j : 0];
+    } else {
+      // tile[c*(NP+1) + r] = B[r][c]  (r = lg < GP rows fit because k <= NP <= ... see dispatch)
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (lg < NP) tile[c * (NP + 1) + lg] = t[c];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NP; ++j) x[j] = alpha * tile[lg * (NP + 1) + j];
+    }
   }
-#pragma unroll
-  for (int j = 0; j < NP; ++j) x[j] *= alpha;
 
   if (OP == TRI_FORWARD || OP == TRI_BOTH) tri_forward<T, NP>(x, Ls, invd);
   if (OP == TRI_BACKWARD || OP == TRI_BOTH) tri_backward<T, NP>(x, Ls, invd);
 
+  if (!LEFT) {
 #pragma unroll
-  for (int j = 0; j < NP; ++j)
-    stg_stream_if(B + (LEFT ? ((long)j + (long)lg * ldb) : ((long)lg + (long)j * ldb)), x[j], have && j < k);
+    for (int j = 0; j < NP; ++j) stg_stream_if(B + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
+  } else {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NP; ++j) tile[lg * (NP + 1) + j] = x[j];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const T out = (lg < NP) ? tile[c * (NP + 1) + lg] : T(0);
+      stg_stream_if(B + (long)lg + (long)c * ldb, out, hrow && c < ncol);
+    }
+  }
 }
 
 }  // namespace kblasx

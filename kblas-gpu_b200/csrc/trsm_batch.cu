@@ -86,7 +86,8 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
   // few right-hand sides and a small factor: pack 4 / 2 matrices per warp
   if (k <= 8 && vec <= 8) return launch_tri_packed<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 8 && vec <= 16) return launch_tri_packed<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
-  if (k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  // (side L reads B by rows, one lane per row: the lane group must cover all k rows)
+  if (!LEFT && k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 16 && vec <= 16) return launch_tri_packed<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
