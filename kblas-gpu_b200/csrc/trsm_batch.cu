@@ -7,6 +7,7 @@
 #include "kblas_common.h"
 #include "kernels/trsm_small.cuh"
 #include "kernels/trsm_blocked.cuh"
+#include "kernels/trsm_reg.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -27,6 +28,20 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
     attr_set = true;
   }
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// k <= 16 and vec <= 16: register-resident, 2 / 4 problems per warp (kernels/trsm_reg.cuh)
+template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_reg(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                          int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;
+  const long wtasks = ((long)batchCount + MPW - 1) / MPW;
+  const long grid = (wtasks + WARPS - 1) / WARPS;
+  tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -83,11 +98,19 @@ static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  // few right-hand sides and a small factor: pack 4 / 2 matrices per warp
+  // few right-hand sides and a small factor: register kernel, 4 / 2 problems per warp
+  // (measured: the shared-memory packed kernel stays ahead only for fp32, side R, 8 < k <= 16)
+  if (h->variant_override != 9 && !(sizeof(T) == 4 && !LEFT && k > 8)) {
+    if (k <= 8 && vec <= 8) return launch_tri_reg<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 8 && vec <= 16) return launch_tri_reg<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 16 && vec <= 16) return launch_tri_reg<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
   if (k <= 8 && vec <= 8) return launch_tri_packed<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 8 && vec <= 16) return launch_tri_packed<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   // (side L reads B by rows, one lane per row: the lane group must cover all k rows)
-  if (!LEFT && k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if constexpr (!LEFT) {
+    if (k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
   if (k <= 16 && vec <= 16) return launch_tri_packed<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
