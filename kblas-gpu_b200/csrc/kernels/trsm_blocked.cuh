@@ -55,7 +55,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
   constexpr int FSZ = NB * NB + NB;
   typedef typename Vec2T<T>::type V2;
   const int g = lane / GP;
-  T *Lkk = Lkk_all + g * FSZ, *invd = Lkk + NB * NB, *S = S_all + g * NB * NB;
+  T *Lkk = Lkk_all + g * FSZ, *invd = Lkk + NB * NB, *S = S_all + g * FSZ;
   const int nblk = (k + NB - 1) / NB;
   for (int bi = 0; bi < nblk; ++bi) {
     const int J = FORWARD ? bi : (nblk - 1 - bi);
@@ -87,7 +87,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       if (FORWARD) {
         // coefficient of x_K[kk] in equation c: L[j0 + c][k0 + kk] = Ts[kk*NB + c]  (axpy form)
 #pragma unroll
-        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * NB * NB, Aq[q], lda, j0, k0, jb, kb, lane);
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, j0, k0, jb, kb, lane);
 #pragma unroll 8
         for (int kk = 0; kk < NB; ++kk) {
           const T m1 = -nx[kk];
@@ -101,7 +101,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       } else {
         // coefficient of x_K[kk] in equation c: L[k0 + kk][j0 + c] = Ts[c*NB + kk]  (dot form)
 #pragma unroll
-        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * NB * NB, Aq[q], lda, k0, j0, kb, jb, lane);
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, k0, j0, kb, jb, lane);
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
           T acc[4] = {T(0), T(0), T(0), T(0)};
@@ -131,7 +131,9 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
 template <typename T, int GP>
 struct TriBlockedSmem {
   static constexpr int NB = 32;
-  static constexpr int per_warp = (32 / GP) * (2 * NB * NB + NB);  // elements of T
+  // the update tiles (S) and the diagonal block (Lkk + invd) are never live at the same time: one
+  // region serves both, which doubles the resident warps (shared memory is the occupancy limiter)
+  static constexpr int per_warp = (32 / GP) * (NB * NB + NB);  // elements of T
 };
 
 // OP: TRI_FORWARD / TRI_BACKWARD / TRI_BOTH (forward with alpha, then backward with 1)
@@ -146,7 +148,7 @@ tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<con
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T *Lkk_all = reinterpret_cast<T *>(smem_raw) + warp * TriBlockedSmem<T, GP>::per_warp;
-  T *S_all = Lkk_all + MPW * FSZ;
+  T *S_all = Lkk_all;  // aliased (see TriBlockedSmem); tile q lives at S_all + q*FSZ
 
   // task = (warp-batch of MPW matrices, slab); slabs == 1 when packed
   const long task = (long)blockIdx.x * WARPS + warp;
