@@ -35,8 +35,11 @@ struct PanelDmmaSmem {
   static constexpr size_t bytes = sizeof(double) * (NB * NB + NB + (size_t)warps * NB * LD);
 };
 
+#ifndef KX_PANEL_WARPS_PER_SM
+#define KX_PANEL_WARPS_PER_SM 8
+#endif
 template <int THREADS, bool STRIDED>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)  // 16 resident warps per SM (<= 128 registers)
+__global__ void __launch_bounds__(THREADS, (32 * KX_PANEL_WARPS_PER_SM) / THREADS)  // resident warps per SM
 potrf_panel_dmma_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, const int batchCount,
                         int *__restrict__ info, const int info_mode) {
   typedef double T;

@@ -143,7 +143,6 @@ tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<con
                          BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
   constexpr int NB = 32;
   constexpr int MPW = 32 / GP;
-  constexpr int FSZ = NB * NB + NB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

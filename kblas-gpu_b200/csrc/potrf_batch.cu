@@ -126,8 +126,9 @@ static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
     if (v != 9) {  // 9 = force the DFMA panel kernel (A/B comparisons)
       // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
       // pivot chain of the diagonal blocks (11..14 = tuning overrides)
-      // measured (B200, batch 64K, n = 64 / 128 / 256): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
-      // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6
+      // measured (B200, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
+      // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6.  One warp with the
+      // cap lifted to 255 registers (8 resident warps per SM, no spills): 5.5 / 9.5 / 14.6
       int threads = 32;
       if (v >= 11 && v <= 14) threads = 32 << (v - 11);
       if (threads == 32) return launch_potrf_panel_dmma<32, STRIDED>(h, "potrf_panel_dmma<T=32>", n, A, lda, batchCount, info);
