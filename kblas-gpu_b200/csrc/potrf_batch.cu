@@ -8,7 +8,7 @@
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
 #include "kernels/potrf_panel.cuh"
-#include "kernels/potrf_panel_dmma.cuh"
+#include "kernels/potrf_panel_mma.cuh"
 #include "potrf_batch.h"
 
 namespace kblasx {
@@ -102,12 +102,13 @@ static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<
   return KBLAS_Success;
 }
 
-// fp64, n > 32: same panel algorithm with the update on the FP64 tensor path (kernels/potrf_panel_dmma.cuh)
-template <int THREADS, bool STRIDED>
-static int launch_potrf_panel_dmma(KBlasHandle *h, const char *name, int n, BatchRef<double, STRIDED> A, int lda,
-                                   int batchCount, int *info) {
-  auto kern = potrf_panel_dmma_kernel<THREADS, STRIDED>;
-  const size_t smem = PanelDmmaSmem<THREADS>::bytes;
+// n > 32, default: same panel algorithm with the update on the mma.sync tensor path -- DMMA for fp64,
+// 3 x TF32 for fp32 (kernels/potrf_panel_mma.cuh)
+template <typename T, int THREADS, bool STRIDED>
+static int launch_potrf_panel_mma(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
+                                  int *info) {
+  auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED>;
+  const size_t smem = PanelMmaSmem<T, THREADS>::bytes;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
@@ -119,35 +120,30 @@ static int launch_potrf_panel_dmma(KBlasHandle *h, const char *name, int n, Batc
   return KBLAS_Success;
 }
 
+#define KX_PANEL_MMA(TH)                                                                                              \
+  launch_potrf_panel_mma<T, TH, STRIDED>(h, sizeof(T) == 8 ? "potrf_panel_dmma<T=" #TH ">" : "potrf_panel_tf32x3<T=" #TH ">", \
+                                         n, A, lda, batchCount, info)
+
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
-  if constexpr (sizeof(T) == 8) {
-    const int v = h->variant_override;
-    if (v != 9) {  // 9 = force the DFMA panel kernel (A/B comparisons)
-      // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
-      // pivot chain of the diagonal blocks (11..14 = tuning overrides)
-      // measured (B200, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
-      // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6.  One warp with the
-      // cap lifted to 255 registers (8 resident warps per SM, no spills): 5.5 / 9.5 / 14.6
-      int threads = 32;
-      if (v >= 11 && v <= 14) threads = 32 << (v - 11);
-      if (threads == 32) return launch_potrf_panel_dmma<32, STRIDED>(h, "potrf_panel_dmma<T=32>", n, A, lda, batchCount, info);
-      if (threads == 64) return launch_potrf_panel_dmma<64, STRIDED>(h, "potrf_panel_dmma<T=64>", n, A, lda, batchCount, info);
-      if (threads == 128) return launch_potrf_panel_dmma<128, STRIDED>(h, "potrf_panel_dmma<T=128>", n, A, lda, batchCount, info);
-      return launch_potrf_panel_dmma<256, STRIDED>(h, "potrf_panel_dmma<T=256>", n, A, lda, batchCount, info);
-    }
-  }
-  // THREADS*2 rows per slab
-  int threads = 32;  // one warp per matrix (measured best for n = 64 / 128 / 256, like the fp64 kernel)
   const int v = h->variant_override;
-  if (v >= 11 && v <= 13) threads = 32 << (v - 11);
+  // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
+  // pivot chain of the diagonal blocks (11..14 = tuning overrides)
+  // measured (B200, fp64, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
+  // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6.  One warp with the
+  // cap lifted to 255 registers (8 resident warps per SM, no spills): 5.5 / 9.5 / 14.6
+  if (v == 12) return KX_PANEL_MMA(64);
+  if (v == 13) return KX_PANEL_MMA(128);
+  if (v == 14) return KX_PANEL_MMA(256);
+  if (v != 9 && (v < 15 || v > 18)) return KX_PANEL_MMA(32);
+  // FMA-pipe panel kernel (A/B comparisons): 9 = one warp, 2 rows per thread
   if constexpr (sizeof(T) == 4) {
     if (v == 15) return launch_potrf_panel<T, 32, 4, STRIDED>(h, "potrf_panel<T=32,R=4>", n, A, lda, batchCount, info);
     if (v == 16) return launch_potrf_panel<T, 64, 4, STRIDED>(h, "potrf_panel<T=64,R=4>", n, A, lda, batchCount, info);
   }
-  if (threads == 32) return launch_potrf_panel<T, 32, 2, STRIDED>(h, "potrf_panel<T=32,R=2>", n, A, lda, batchCount, info);
-  if (threads == 64) return launch_potrf_panel<T, 64, 2, STRIDED>(h, "potrf_panel<T=64,R=2>", n, A, lda, batchCount, info);
-  return launch_potrf_panel<T, 128, 2, STRIDED>(h, "potrf_panel<T=128,R=2>", n, A, lda, batchCount, info);
+  if (v == 17) return launch_potrf_panel<T, 64, 2, STRIDED>(h, "potrf_panel<T=64,R=2>", n, A, lda, batchCount, info);
+  if (v == 18) return launch_potrf_panel<T, 128, 2, STRIDED>(h, "potrf_panel<T=128,R=2>", n, A, lda, batchCount, info);
+  return launch_potrf_panel<T, 32, 2, STRIDED>(h, "potrf_panel<T=32,R=2>", n, A, lda, batchCount, info);
 }
 
 // Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)

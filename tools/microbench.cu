@@ -169,6 +169,34 @@ __global__ void k_dmma(double *out, int iters, long long *cyc, int ilp) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// legacy tensor path, TF32 m16n8k8 (fp32 accumulate): rate and latency (3 of these emulate one fp32 product)
+__global__ void k_tf32mma(float *out, int iters, long long *cyc, int ilp) {
+  unsigned a[4], b[2];
+  for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(out[i] + threadIdx.x) & 0xffffe000u;
+  for (int i = 0; i < 2; ++i) b[i] = __float_as_uint(out[i] - threadIdx.x) & 0xffffe000u;
+  float c[8][4];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (u < ilp)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[u][0]), "+f"(c[u][1]), "+f"(c[u][2]), "+f"(c[u][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s += c[u][0] + c[u][1] + c[u][2] + c[u][3];
+  out[8 + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 int main(int argc, char **argv) {
   const char *part = argc > 1 ? argv[1] : "B";
   int gran = argc > 2 ? atoi(argv[2]) : 0;
@@ -256,6 +284,13 @@ int main(int argc, char **argv) {
       CK(cudaMemcpy(hc, cyc, 8, cudaMemcpyDeviceToHost));
       printf("DMMA m8n8k4 ilp=%d, %d warps: %.2f cycles per DMMA per warp, %.1f FMA/clk/SM\n", ilp, th / 32,
              (double)hc[0] / (it * (double)ilp), it * (double)ilp * (th / 32) * 256.0 / hc[0]);
+    }
+  for (int ilp = 1; ilp <= 8; ilp *= 2)
+    for (int th = 32; th <= 1024; th *= 4) {
+      k_tf32mma<<<1, th>>>(reinterpret_cast<float *>(out), it, cyc, ilp);
+      CK(cudaMemcpy(hc, cyc, 8, cudaMemcpyDeviceToHost));
+      printf("TF32 mma.sync m16n8k8 ilp=%d, %d warps: %.2f cycles per MMA per warp, %.1f MAC/clk/SM\n", ilp, th / 32,
+             (double)hc[0] / (it * (double)ilp), it * (double)ilp * (th / 32) * 1024.0 / hc[0]);
     }
   printf("SM clock %d kHz, SMs %d\n", prop.clockRate, prop.multiProcessorCount);
   return 0;

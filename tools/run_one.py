@@ -23,8 +23,8 @@ for it in range(2):
         h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
         rc = h.trsm_batch_strided(s, "L", t, "N", m, n, 0.28, A, n, n * n, B, m, m * n, batch)
     else:
-        pa = (A.data_ptr() + torch.arange(batch, device="cuda") * (n * n * 8)).contiguous()
-        pb = (B.data_ptr() + torch.arange(batch, device="cuda") * (m * n * 8)).contiguous()
+        pa = (A.data_ptr() + torch.arange(batch, device="cuda") * (n * n * A.element_size())).contiguous()
+        pb = (B.data_ptr() + torch.arange(batch, device="cuda") * (m * n * B.element_size())).contiguous()
         rc = h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, None) if op == "posv_ptr" else h.potrf_batch("L", n, pa, n, batch, None)
     torch.cuda.synchronize()
     assert rc == 1, rc
