@@ -8,6 +8,7 @@
 #include "kernels/trsm_small.cuh"
 #include "kernels/trsm_blocked.cuh"
 #include "kernels/trsm_reg.cuh"
+#include "kernels/trsm_bcast.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -41,6 +42,20 @@ static int launch_tri_reg(KBlasHandle *h, const char *name, int k, int vec, T al
   const long wtasks = ((long)batchCount + MPW - 1) / MPW;
   const long grid = (wtasks + WARPS - 1) / WARPS;
   tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// k <= 16 and vec <= 16: factor read as L1-broadcast vector loads, 2 / 4 problems per warp (kernels/trsm_bcast.cuh)
+template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_bcast(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                            int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;  // measured: 2 / 4 / 8 warps per CTA within +-3 %
+  const long wtasks = ((long)batchCount + MPW - 1) / MPW;
+  const long grid = (wtasks + WARPS - 1) / WARPS;
+  tri_solve_bcast_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
       <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
@@ -100,6 +115,16 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
   // few right-hand sides and a small factor: register kernel, 4 / 2 problems per warp
   // (measured: the shared-memory packed kernel stays ahead only for fp32, side R, 8 < k <= 16)
+  // full 8 / 16 columns with 16-byte aligned columns: factor read as L1-broadcast vector loads
+  // (pointer-array entries are checked in the kernel); ragged k or odd lda: register/shuffle kernel
+  bool vec_ok = (k == 8 || k == 16) && ((size_t)lda * sizeof(T)) % 16 == 0;
+  if constexpr (STRIDED) vec_ok = vec_ok && (reinterpret_cast<size_t>(A.base) % 16 == 0) && ((size_t)A.stride * sizeof(T)) % 16 == 0;
+  if (vec_ok && h->variant_override != 9 && h->variant_override != 8) {
+    if (k <= 8 && vec <= 8) return launch_tri_bcast<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 8 && vec <= 16) return launch_tri_bcast<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 16 && vec <= 16) return launch_tri_bcast<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
+  // 8 = the register/shuffle kernel (A/B comparisons)
   if (h->variant_override != 9 && !(sizeof(T) == 4 && !LEFT && k > 8)) {
     if (k <= 8 && vec <= 8) return launch_tri_reg<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 8 && vec <= 16) return launch_tri_reg<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);

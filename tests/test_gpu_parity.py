@@ -226,6 +226,47 @@ def test_trsm_large_k(env, p, side, trans, k, other):
     assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
+@pytest.mark.parametrize("k,vec", [(8, 8), (8, 5), (8, 16), (16, 16), (16, 3)])
+@pytest.mark.parametrize("layout", ["strided", "ptr_aligned", "ptr_offset1"])
+def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout):
+    """lda == k (the north-star layout): the L1-broadcast kernel; strided, pointer array, and a pointer array whose
+    entries are NOT 16-byte aligned (one element past an aligned address: the kernel's scalar path)."""
+    kb, h, torch = env
+    dt = DT[p]
+    m, n = (k, vec) if side == "L" else (vec, k)
+    batch, alpha = 131, -1.7
+    A = U.rand_spd_batch(batch, k, dtype=dt, seed=k + 3)           # lda = k, stride k*k
+    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=m * 10 + n)      # ldb = m
+    Bo = B0.copy()
+    U.oracle_trsm(side, "L", trans, "N", m, n, alpha, A, Bo)
+    es = np.dtype(dt).itemsize
+    off = 1 if layout == "ptr_offset1" else 0
+    # device copies with `off` elements of slack in front so that every matrix starts off-by-one
+    dA = torch.zeros(A.size + 4, dtype=getattr(torch, np.dtype(dt).name), device="cuda")
+    dB = torch.zeros(B0.size + 4, dtype=dA.dtype, device="cuda")
+    dA[off:off + A.size] = _dev(torch, A).flatten()
+    dB[off:off + B0.size] = _dev(torch, B0).flatten()
+    h.trsm_batch_wsquery(side, m, n, batch)
+    h.trsm_batch_strided_wsquery(side, m, n, batch)
+    h.allocate_workspace()
+    if layout == "strided":
+        rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, alpha, dA, k, k * k, dB, m, m * n, batch)
+    else:
+        perm = torch.randperm(batch, device="cuda")
+        pa = (dA.data_ptr() + (off + perm * (k * k)) * es).contiguous()
+        pb = (dB.data_ptr() + (off + perm * (m * n)) * es).contiguous()
+        rc = h.trsm_batch(side, "L", trans, "N", m, n, alpha, pa, k, pb, m, batch, prec=p)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    assert ("tri_bcast" in h.last_kernel) == (k in (8, 16)), h.last_kernel
+    got = dB[off:off + B0.size].cpu().numpy().reshape(B0.shape)
+    assert np.abs(got - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
+    assert np.array_equal(dA[off:off + A.size].cpu().numpy().reshape(A.shape), A), "A is read-only"
+    assert float(dB[:off].abs().sum()) == 0 and float(dB[off + B0.size:].abs().sum()) == 0, "slack untouched"
+
+
 def test_trsm_potrs_posv_return_codes(env):
     kb, h, torch = env
     dA, dB = _dev(torch, U.rand_spd_batch(2, 8)), _dev(torch, U.rand_batch(2, 8, 8))

@@ -82,28 +82,33 @@ def main():
                 h.destroy()
                 del P, A, B0, B
     else:
+        ns = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 16, 8]
         for prec, dt, es in (("D", torch.float64, 8), ("S", torch.float32, 4)):
-            for n in (32, 16, 8):
+            for n in ns:
                 m = n
                 P = bench.make_spd(torch, batch, n, dt, 1)
                 L = P.clone()
-                h = kb.Handle()
-                h.potrf_batch_strided("L", n, L, n, n * n, batch, None)
+                h0 = kb.Handle()
+                h0.potrf_batch_strided("L", n, L, n, n * n, batch, None)
+                h0.destroy()
                 B0 = torch.rand((batch, n, m), device="cuda", dtype=dt)
                 B = torch.empty_like(B0)
                 algo_trs = (n * (n + 1) // 2 + 2 * m * n) * es
-                for name, fn in (
-                    ("potrs_R", lambda: h.potrs_batch_strided("R", "L", m, n, L, n, n * n, B, m, m * n, batch)),
-                    ("trsm_LLN", lambda: h.trsm_batch_strided("L", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
-                    ("trsm_LLT", lambda: h.trsm_batch_strided("L", "L", "T", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
-                    ("trsm_RLN", lambda: h.trsm_batch_strided("R", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
-                    ("trsm_RLT", lambda: h.trsm_batch_strided("R", "L", "T", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
-                ):
-                    best, mean = timeit(fn, lambda: B.copy_(B0))
-                    print(json.dumps({"op": f"{prec}{name}", "n": n, "m": m, "kernel": h.last_kernel, "ms_best": best,
-                                      "ms_mean": mean, "Mprob_s": batch / best / 1e3, "algo_GBs": batch * algo_trs / best / 1e6,
-                                      "frac": batch * algo_trs / best / 1e6 / PEAK}), flush=True)
-                h.destroy()
+                for v in variants:
+                    os.environ["KBLAS_B200_VARIANT"] = str(v)
+                    h = kb.Handle()
+                    for name, fn in (
+                        ("potrs_R", lambda: h.potrs_batch_strided("R", "L", m, n, L, n, n * n, B, m, m * n, batch)),
+                        ("trsm_LLN", lambda: h.trsm_batch_strided("L", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
+                        ("trsm_LLT", lambda: h.trsm_batch_strided("L", "L", "T", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
+                        ("trsm_RLN", lambda: h.trsm_batch_strided("R", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
+                        ("trsm_RLT", lambda: h.trsm_batch_strided("R", "L", "T", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
+                    ):
+                        best, mean = timeit(fn, lambda: B.copy_(B0))
+                        print(json.dumps({"op": f"{prec}{name}", "n": n, "m": m, "variant": v, "kernel": h.last_kernel, "ms_best": best,
+                                          "ms_mean": mean, "Mprob_s": batch / best / 1e3, "algo_GBs": batch * algo_trs / best / 1e6,
+                                          "frac": batch * algo_trs / best / 1e6 / PEAK}), flush=True)
+                    h.destroy()
                 del P, L, B0, B
 
 
