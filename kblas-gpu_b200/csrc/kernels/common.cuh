@@ -66,6 +66,15 @@ __device__ __forceinline__ void stg_stream_if(float *p, float v, bool pred) {
                ::"l"(p), "f"(v), "r"((int)pred) : "memory");
 }
 
+// Hide a pointer's provenance from the optimiser.  Without it NVVM keeps every address it has computed
+// alive for a later re-use (the 64 column addresses of a forward pass for the backward pass of POTRS, load
+// addresses for the stores): hundreds of registers, or kilobytes of spills under a cap.
+template <typename T>
+__device__ __forceinline__ T *launder(T *p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // ---- shared-memory pair loads -----------------------------------------------------------
 // asm volatile on purpose: the staged factor is immutable, and a plain (const __restrict__)
 // load lets the compiler keep every value it has ever read alive in registers across the

@@ -36,13 +36,6 @@ template <int OFF>
 __device__ __forceinline__ void ldg_bcast_vec(float (&v)[4], const float *p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4 + %5];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "n"(OFF));
 }
-// hide a pointer's provenance from the optimiser: without it the 64 column addresses of the forward
-// pass are kept alive (CSE) for the backward pass of POTRS -- 1.6 KB of spills
-template <typename T>
-__device__ __forceinline__ const T *launder(const T *p) {
-  asm volatile("" : "+l"(p));
-  return p;
-}
 __device__ __forceinline__ void ldg_cached_if(double &v, const double *p, bool pred) {
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.global.nc.f64 %0, [%1]; }" : "+d"(v) : "l"(p), "r"((int)pred));
 }

@@ -9,6 +9,7 @@
 #include "kernels/trsm_blocked.cuh"
 #include "kernels/trsm_reg.cuh"
 #include "kernels/trsm_bcast.cuh"
+#include "kernels/trsm_dual.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -29,6 +30,27 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
     attr_set = true;
   }
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// side R, full NP x NP factor: two vectors per lane, two problems per warp, cp.async staging (kernels/trsm_dual.cuh)
+template <typename T, int NP, int OP, bool STRIDED>
+static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                           BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4;
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
+  const size_t smem = (size_t)WARPS * 2 * TriDualSmem<T, NP>::per_problem * sizeof(T);
+  auto kern = tri_solve_dual_kernel<T, NP, OP, WARPS, STRIDED>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
+    attr_set = true;
+  }
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -123,6 +145,13 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
     if (k <= 8 && vec <= 8) return launch_tri_bcast<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 8 && vec <= 16) return launch_tri_bcast<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 16 && vec <= 16) return launch_tri_bcast<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
+  if constexpr (!LEFT) {
+    if (h->variant_override != 9 && h->variant_override != 8) {
+      if (k == 16) return launch_tri_dual<T, 16, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
+      if (k == 24) return launch_tri_dual<T, 24, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
+      if (k == 32) return launch_tri_dual<T, 32, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
+    }
   }
   // 8 = the register/shuffle kernel (A/B comparisons)
   if (h->variant_override != 9 && !(sizeof(T) == 4 && !LEFT && k > 8)) {

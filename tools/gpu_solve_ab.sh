@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "small_packed" 2>&1 | tail -5
-python tools/bench_variants.py -1,7,6 solve 16,8 > gpurun_out/t_solve_ab.jsonl 2>gpurun_out/t_solve_ab.err; tail -3 gpurun_out/t_solve_ab.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "trsm or potrs or posv" 2>&1 | tail -5
+python tools/bench_variants.py -1,8 solve 32 > gpurun_out/t_solve_ab.jsonl 2>gpurun_out/t_solve_ab.err; tail -3 gpurun_out/t_solve_ab.err
 python - <<'PY'
 import json
 for l in open('gpurun_out/t_solve_ab.jsonl'):
