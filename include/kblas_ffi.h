@@ -85,4 +85,19 @@ const char *kblasx_version(void);
 int         kblasx_reg_size(int n);
 int         kblasx_closest_reg_size(int n);
 
+
+/* (4) host-memory entry points: no reference counterpart (the reference takes device pointers only; its
+ *     callers cudaMemcpy whole arrays around the call, testing/batch_triangular/test_Xpotrf_batch.cpp:170-206).
+ *  Strided batch Cholesky of matrices that live in HOST memory (pinned for full speed): 256 MiB chunks
+ *  through three device staging buffers on three streams, so H2D, the kernel and D2H overlap.
+ *  Synchronous: the result is in A_out on return.  A_out == A_in is the in-place LAPACK form and is
+ *  bit-identical to cudaMemcpy + kblas?potrf_batch_strided + cudaMemcpy.  info_host is written only in
+ *  KBLAS_B200_INFO_MODE=lapack.  KBLAS_B200_HOSTCOPY=tri moves only the lower triangle (strided 3-D
+ *  copies; measured slower on PCIe Gen5, see csrc/host_pipeline.cu); out of place it then leaves the
+ *  elements of A_out above the diagonal 8 x 8 blocks unwritten. */
+int kblasxSpotrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const float *A_in, float *A_out,
+                                    int lda, long strideA, int batchCount, int *info_host);
+int kblasxDpotrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const double *A_in, double *A_out,
+                                    int lda, long strideA, int batchCount, int *info_host);
+
 #endif /* KBLAS_B200_FFI_H */

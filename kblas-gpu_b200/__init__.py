@@ -88,6 +88,7 @@ _sig("kblasx_version", C.c_char_p)
 _sig("kblasx_reg_size", _i, _i)
 _sig("kblasx_closest_reg_size", _i, _i)
 for _p, _t in (("S", C.c_float), ("D", C.c_double)):
+    _sig(f"kblasx{_p}potrf_batch_strided_host", _i, _H, _c, _i, _P, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}potrf_batch", _i, _H, _c, _i, _P, _i, _i, _P)
     _sig(f"kblas{_p}potrf_batch_strided", _i, _H, _c, _i, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}trsm_batch", _i, _H, _c, _c, _c, _c, _i, _i, _t, _P, _i, _P, _i, _i)
@@ -109,15 +110,25 @@ def _ptr(x):
     return int(x)
 
 
+def _hptr(x):
+    """host address of a CPU torch tensor / numpy array / int / None"""
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    return int(x)
+
+
 def _prec(x, prec=None):
     """'S' or 'D' from an explicit flag or a torch dtype"""
     if prec is not None:
         return prec.upper()
-    import torch
-
-    if x.dtype == torch.float64:
+    name = str(x.dtype).replace("torch.", "")
+    if name == "float64":
         return "D"
-    if x.dtype == torch.float32:
+    if name == "float32":
         return "S"
     raise TypeError(f"unsupported dtype {x.dtype}: this path implements s and d precision only")
 
@@ -280,6 +291,13 @@ class Handle:
         f = getattr(_lib, f"kblas{_prec(B, prec)}posv_batch_strided")
         return f(self._h, _ch(side), _ch(uplo), m, n, _ptr(A), lda, strideA, _ptr(B), ldb, strideB, batch,
                  _ptr(info))
+
+    # -- compute: matrices in HOST memory (pinned for full speed); no reference counterpart ----
+    def potrf_batch_strided_host(self, uplo, n, A_in, A_out, lda, strideA, batch, info=None, prec=None):
+        """chunked H2D / potrf / D2H pipeline; only the lower triangle crosses PCIe (csrc/host_pipeline.cu).
+        A_in / A_out: CPU torch tensors, numpy arrays or raw host addresses; A_out may be A_in."""
+        f = getattr(_lib, f"kblasx{_prec(A_in, prec)}potrf_batch_strided_host")
+        return f(self._h, _ch(uplo), n, _hptr(A_in), _hptr(A_out), lda, strideA, batch, _hptr(info))
 
     # -- compute: pointer arrays (device arrays of device pointers) -----------------------
     def potrf_batch(self, uplo, n, A_array, lda, batch, info=None, prec="D"):

@@ -208,6 +208,7 @@ KBlasHandle::KBlasHandle(int /*use_magma*/, cudaStream_t stream_, int device_id_
   variant_override = vo ? atoi(vo) : -1;
   launch_count = 0;
   last_kernel = "none";
+  host_pipe = NULL;
 }
 
 // minimal lazily-bound cuBLAS (only for kblasGetCublasHandle / kblasSetStream parity)
@@ -233,7 +234,10 @@ struct LazyCublas {
 } g_cublas;
 }  // namespace
 
+namespace kblasx { void host_pipe_destroy(void *p); }  // host_pipeline.cu
+
 KBlasHandle::~KBlasHandle() {
+  kblasx::host_pipe_destroy(host_pipe);
   if (cublas_handle != NULL && create_cublas && g_cublas.destroy) g_cublas.destroy(cublas_handle);
   for (int i = 0; i < nStreams; ++i) check_error(cudaStreamDestroy(streams[i]));
   timer.destroy();

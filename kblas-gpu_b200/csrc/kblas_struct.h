@@ -126,6 +126,7 @@ struct KBlasHandle {
   int variant_override;    // -1 = auto; tuning / ablation hook (env KBLAS_B200_VARIANT)
   long launch_count;       // kernels launched through this handle
   const char *last_kernel; // name of the last dispatched kernel variant
+  void *host_pipe;         // staging buffers / streams of the host-memory entry points (host_pipeline.cu), lazily created
 
   explicit KBlasHandle(int use_magma, cudaStream_t stream = 0, int device_id = 0);
   ~KBlasHandle();

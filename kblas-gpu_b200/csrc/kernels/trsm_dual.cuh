@@ -36,15 +36,24 @@ struct TriDualSmem {
                 "the two factor copies of a warp must sit a non-zero multiple of 16 B apart (mod 128)");
 };
 
+#ifndef KX_DUAL_MINB64
+#define KX_DUAL_MINB64 2
+#endif
+#ifndef KX_DUAL_FENCE64
+#define KX_DUAL_FENCE64 2
+#endif
+#ifndef KX_DUAL_FENCE32
+#define KX_DUAL_FENCE32 4
+#endif
 template <typename T, int NP, int OP, int WARPS, bool STRIDED>
-__global__ void __launch_bounds__(WARPS * 32, sizeof(T) == 8 ? 2 : (NP > 24 ? 3 : 4))
+__global__ void __launch_bounds__(WARPS * 32, sizeof(T) == 8 ? KX_DUAL_MINB64 : (NP > 24 ? 3 : 4))
 tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda, BatchRef<T, STRIDED> Bref,
                       const int ldb, const int batchCount, const int slabs) {
   constexpr int VW = 16 / (int)sizeof(T);
   constexpr int NV = NP / VW;
   constexpr int SE = SectorElems<T>::value;
   constexpr int FSZ = TriDualSmem<T, NP>::per_problem;
-  constexpr int FENCE = sizeof(T) == 8 ? 2 : 4;  // columns between scheduling fences (bounds ptxas' LDS look-ahead)
+  constexpr int FENCE = sizeof(T) == 8 ? KX_DUAL_FENCE64 : KX_DUAL_FENCE32;  // columns between scheduling fences (bounds ptxas' LDS look-ahead)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

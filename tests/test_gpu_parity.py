@@ -177,6 +177,44 @@ def test_potrf_lapack_info_mode_is_opt_in(env):
     h.destroy()
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n,lda,extra", [(32, 32, 0), (32, 34, 1), (20, 20, 0), (8, 8, 0), (40, 40, 0), (16, 16, 2)])
+@pytest.mark.parametrize("mode", ["tri", "full"])
+def test_potrf_host_pipeline(env, p, n, lda, extra, mode, monkeypatch):
+    """kblasx?potrf_batch_strided_host (host memory in, host memory out; chunked 3-stream pipeline, lower-triangle
+    transfers) == H2D + kblas?potrf_batch_strided + D2H, bit for bit, in place and out of place."""
+    kb, h, torch = env
+    dt = DT[p]
+    batch = 301
+    A0 = U.rand_spd_batch(batch, n, lda=lda, dtype=dt, seed=n + 5, extra_cols=extra)
+    stride = (n + extra) * lda
+    # device path
+    dA = _dev(torch, A0)
+    h.potrf_batch_strided_wsquery(n, batch)
+    h.allocate_workspace()
+    assert h.potrf_batch_strided("L", n, dA, lda, stride, batch, None) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    want = dA.cpu().numpy()
+    # host path: ~6 matrices per chunk -> dozens of chunks through the 3 staging buffers
+    monkeypatch.setenv("KBLAS_B200_HOSTCHUNK_MB", str(6.5 * stride * np.dtype(dt).itemsize / (1 << 20)))
+    monkeypatch.setenv("KBLAS_B200_HOSTCOPY", mode)
+    inplace = A0.copy()
+    assert h.potrf_batch_strided_host("L", n, inplace, inplace, lda, stride, batch) == kb.KBLAS_Success
+    assert np.array_equal(inplace, want)
+    out = np.full_like(A0, 9.5)
+    src = A0.copy()
+    assert h.potrf_batch_strided_host("L", n, src, out, lda, stride, batch) == kb.KBLAS_Success
+    assert np.array_equal(src, A0), "A_in is read-only"
+    M, W = U.as_mats(out, n, n), U.as_mats(want, n, n)
+    assert np.array_equal(np.tril(M), np.tril(W))
+    if mode == "tri" and n > 8 and extra == 0:
+        # above the diagonal 8 x 8 blocks nothing is written
+        i, j = np.indices((n, n))
+        untouched = (j // 8) > (i // 8)          # as_mats gives [b, row, col]
+        assert (M[:, untouched] == 9.5).all()
+    assert h.potrf_batch_strided_host("U", n, src, out, lda, stride, batch) == kb.KBLAS_NotImplemented
+
+
 # =============================================================================================
 # trsm / potrs / posv
 @pytest.mark.parametrize("p", ["D", "S"])
