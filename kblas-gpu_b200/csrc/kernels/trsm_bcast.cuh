@@ -23,6 +23,10 @@
 #include "common.cuh"
 #include "trsm_small.cuh"  // TriOp, sched_fence
 
+#ifndef KX_BCAST_FP_SCALE
+#define KX_BCAST_FP_SCALE 1
+#endif
+
 namespace kblasx {
 
 // L1-cached (read-only path) loads of the factor.  asm volatile: the forward and the backward pass
@@ -103,7 +107,7 @@ __device__ __forceinline__ void tri_bcast_solve_body(T (&x)[NP], const T *__rest
   constexpr int NV = NP / VW;
   // ptxas hoists every load of the unrolled substitution to the top (250+ registers, or KBs of spills
   // under a cap): a scheduling fence every FP columns bounds the loads in flight to ~32 registers
-  constexpr int FP = (8 / NV) > 0 ? (8 / NV) : 1;
+  constexpr int FP = ((8 / NV) > 0 ? (8 / NV) : 1) * KX_BCAST_FP_SCALE;
   if (OP == TRI_FORWARD || OP == TRI_BOTH) {
     const T *col = launder(A);
 #pragma unroll

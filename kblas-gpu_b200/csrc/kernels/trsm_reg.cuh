@@ -20,7 +20,7 @@
 namespace kblasx {
 
 template <typename T, int NP, int GP, bool LEFT, int OP, int WARPS, bool STRIDED>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, OP == TRI_BOTH ? 1 : (sizeof(T) * NP > 64 ? 24 : 32) / WARPS)  // <= 80 / 64 registers
 tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                      BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount) {
   static_assert(NP <= GP, "one lane per factor row");
@@ -99,9 +99,10 @@ tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T
     }
   }
 
+  T *Bs = launder(B);  // fresh store addresses: the 16 load addresses would otherwise stay live through the solve
   if (!LEFT) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) stg_stream_if(B + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
+    for (int j = 0; j < NP; ++j) stg_stream_if(Bs + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
   } else {
     __syncwarp();
 #pragma unroll
@@ -110,7 +111,7 @@ tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const T out = (lg < NP) ? tile[c * (NP + 1) + lg] : T(0);
-      stg_stream_if(B + (long)lg + (long)c * ldb, out, hrow && c < ncol);
+      stg_stream_if(Bs + (long)lg + (long)c * ldb, out, hrow && c < ncol);
     }
   }
 }

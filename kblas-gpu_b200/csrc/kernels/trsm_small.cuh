@@ -208,9 +208,10 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
   if (OP == TRI_FORWARD || OP == TRI_BOTH) tri_forward<T, NP>(x, Ls, invd);
   if (OP == TRI_BACKWARD || OP == TRI_BOTH) tri_backward<T, NP>(x, Ls, invd);
 
+  T *Bs = launder(B);  // fresh store addresses (common.cuh: launder)
   if (!LEFT) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) stg_stream_if(B + my + (long)j * ldb, x[j], my < vec && j < k);
+    for (int j = 0; j < NP; ++j) stg_stream_if(Bs + my + (long)j * ldb, x[j], my < vec && j < k);
   } else {
     __syncwarp();
 #pragma unroll
@@ -220,7 +221,7 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
     for (int c = 0; c < 32; ++c) {
       const int colB = v0 + c;
       const T out = (lane < NP) ? tile[c * TS + lane] : T(0);  // lanes >= NP would read past the tile
-      stg_stream_if(B + lane + (long)colB * ldb, out, lane < k && colB < vec);
+      stg_stream_if(Bs + lane + (long)colB * ldb, out, lane < k && colB < vec);
     }
   }
 }
@@ -296,9 +297,10 @@ tri_solve_packed_kernel(const int k, const int vec, const T alpha, BatchRef<cons
   if (OP == TRI_FORWARD || OP == TRI_BOTH) tri_forward<T, NP>(x, Ls, invd);
   if (OP == TRI_BACKWARD || OP == TRI_BOTH) tri_backward<T, NP>(x, Ls, invd);
 
+  T *Bs = launder(B);  // fresh store addresses (common.cuh: launder)
   if (!LEFT) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) stg_stream_if(B + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
+    for (int j = 0; j < NP; ++j) stg_stream_if(Bs + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
   } else {
     __syncwarp();
 #pragma unroll
@@ -307,7 +309,7 @@ tri_solve_packed_kernel(const int k, const int vec, const T alpha, BatchRef<cons
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const T out = (lg < NP) ? tile[c * (NP + 1) + lg] : T(0);
-      stg_stream_if(B + (long)lg + (long)c * ldb, out, hrow && c < ncol);
+      stg_stream_if(Bs + (long)lg + (long)c * ldb, out, hrow && c < ncol);
     }
   }
 }

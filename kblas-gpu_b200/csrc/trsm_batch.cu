@@ -137,24 +137,28 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
   // few right-hand sides and a small factor: register kernel, 4 / 2 problems per warp
   // (measured: the shared-memory packed kernel stays ahead only for fp32, side R, 8 < k <= 16)
-  // full 8 / 16 columns with 16-byte aligned columns: factor read as L1-broadcast vector loads
-  // (pointer-array entries are checked in the kernel); ragged k or odd lda: register/shuffle kernel
+  // Full 8 / 16 columns with 16-byte aligned columns can read the factor as L1-broadcast vector loads
+  // (kernels/trsm_bcast.cuh; pointer-array entries are checked in the kernel).  Measured on B200 (batch 2^20):
+  // it wins where the register/shuffle kernel runs out of registers -- fp64 potrs k = 16: 1.58 vs 2.74 ms --
+  // and loses by 3-10 % elsewhere (the shuffle kernel at <= 80 registers: dtrsm R k=16 1.03-1.06 ms), so
+  // that is the only case it takes by default; variant 7 forces it everywhere.
   bool vec_ok = (k == 8 || k == 16) && ((size_t)lda * sizeof(T)) % 16 == 0;
   if constexpr (STRIDED) vec_ok = vec_ok && (reinterpret_cast<size_t>(A.base) % 16 == 0) && ((size_t)A.stride * sizeof(T)) % 16 == 0;
-  if (vec_ok && h->variant_override != 9 && h->variant_override != 8) {
+  const bool bcast_default = (OP == TRI_BOTH) && sizeof(T) == 8 && k == 16;
+  if (vec_ok && h->variant_override != 9 && h->variant_override != 8 && (bcast_default || h->variant_override == 7)) {
     if (k <= 8 && vec <= 8) return launch_tri_bcast<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 8 && vec <= 16) return launch_tri_bcast<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 16 && vec <= 16) return launch_tri_bcast<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   }
   if constexpr (!LEFT) {
     if (h->variant_override != 9 && h->variant_override != 8) {
-      if (k == 16) return launch_tri_dual<T, 16, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
+      if (k == 16 && vec > 16) return launch_tri_dual<T, 16, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
       if (k == 24) return launch_tri_dual<T, 24, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
       if (k == 32) return launch_tri_dual<T, 32, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
     }
   }
   // 8 = the register/shuffle kernel (A/B comparisons)
-  if (h->variant_override != 9 && !(sizeof(T) == 4 && !LEFT && k > 8)) {
+  if (h->variant_override != 9 && (h->variant_override == 6 || !(sizeof(T) == 4 && !LEFT && k > 8))) {
     if (k <= 8 && vec <= 8) return launch_tri_reg<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 8 && vec <= 16) return launch_tri_reg<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 16 && vec <= 16) return launch_tri_reg<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);

@@ -268,10 +268,13 @@ def test_trsm_large_k(env, p, side, trans, k, other):
 @pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
 @pytest.mark.parametrize("k,vec", [(8, 8), (8, 5), (8, 16), (16, 16), (16, 3)])
 @pytest.mark.parametrize("layout", ["strided", "ptr_aligned", "ptr_offset1"])
-def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout):
-    """lda == k (the north-star layout): the L1-broadcast kernel; strided, pointer array, and a pointer array whose
-    entries are NOT 16-byte aligned (one element past an aligned address: the kernel's scalar path)."""
-    kb, h, torch = env
+def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout, monkeypatch):
+    """lda == k (the north-star layout) on the L1-broadcast kernel (forced: by default it only serves fp64 potrs
+    k = 16); strided, pointer array, and a pointer array whose entries are NOT 16-byte aligned (one element past
+    an aligned address: the kernel's scalar path)."""
+    kb, _, torch = env
+    monkeypatch.setenv("KBLAS_B200_VARIANT", "7")
+    h = kb.Handle()
     dt = DT[p]
     m, n = (k, vec) if side == "L" else (vec, k)
     batch, alpha = 131, -1.7
@@ -303,6 +306,7 @@ def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout):
     assert np.abs(got - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
     assert np.array_equal(dA[off:off + A.size].cpu().numpy().reshape(A.shape), A), "A is read-only"
     assert float(dB[:off].abs().sum()) == 0 and float(dB[off + B0.size:].abs().sum()) == 0, "slack untouched"
+    h.destroy()
 
 
 def test_trsm_potrs_posv_return_codes(env):

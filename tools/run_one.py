@@ -8,6 +8,7 @@ kb = importlib.import_module("kblas-gpu_b200")
 op, n = sys.argv[1], int(sys.argv[2])
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 18
 dt = torch.float32 if os.environ.get("F32") else torch.float64
+prec = "S" if os.environ.get("F32") else "D"
 m = (16 if op.endswith("ptr") else n)
 P = bench.make_spd(torch, batch, n, dt, 1)
 B = torch.rand((batch, n, m), device="cuda", dtype=dt)
@@ -25,7 +26,8 @@ for it in range(2):
     else:
         pa = (A.data_ptr() + torch.arange(batch, device="cuda") * (n * n * A.element_size())).contiguous()
         pb = (B.data_ptr() + torch.arange(batch, device="cuda") * (m * n * B.element_size())).contiguous()
-        rc = h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, None) if op == "posv_ptr" else h.potrf_batch("L", n, pa, n, batch, None)
+        rc = (h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, None, prec=prec) if op == "posv_ptr"
+              else h.potrf_batch("L", n, pa, n, batch, None, prec=prec))
     torch.cuda.synchronize()
     assert rc == 1, rc
 print("ok", h.last_kernel)
