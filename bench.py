@@ -9,9 +9,10 @@ of the HBM roofline.  One "step" = one kblasDpotrf_batch_strided call over the w
 synthetic random SPD matrices (uniform [0,1) + n*I, the reference harness's distribution,
 testing/testing_helper.cu:353-402).
   * N = 1: batch = 2^20 (configs[1] at n = 32, the configuration the metric is quoted on).
-  * N > 1: batch = 2^23 split by contiguous slab over the ranks (configs[4], "strong" scaling:
-    total work fixed); no data-path collective exists -- torch.distributed only provides the
-    barrier and the max-over-ranks reduction of the device time.
+  * N > 1: batch = N * 2^20 split by contiguous slab over the ranks ("weak" scaling: 2^20 matrices
+    per GPU at every N; at N = 8 this is exactly configs[4], 8M matrices over the 8 GPUs of a
+    box); no data-path collective exists -- torch.distributed only provides the barrier and the
+    max-over-ranks reduction of the device time.
 Prints ONE JSON line on rank 0.  `value` is device-resident throughput (inputs in HBM, CUDA-event
 timed on the launching stream, max over ranks); `e2e` is the same call with HOST (pinned) buffers,
 host<->device copies inside the timed region.  `roofline` uses the algorithmic bytes of SURVEY.md
@@ -271,7 +272,7 @@ def main():
         v = len(vals) * sample / sum(sample / x for x in vals)
         line = {"impl": "reference", "metric": "dpotrf_batch_strided n=32 fp64 throughput", "value": v, "unit": "matrices/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * sample / v, "higher_is_better": True,
-                "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"reference harness CPU LAPACK dpotrf loop, n=32 fp64, sample {sample} matrices/step"},
                 "cpu_baseline": {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
                                  "sample": f"{sample} matrices per step"},
@@ -290,7 +291,7 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    total_batch = args.batch or ((1 << 20) if world == 1 else (1 << 23))
+    total_batch = args.batch or (world << 20)
     slab = importlib.import_module("kblas-gpu_b200.slab")
     b0, b1 = slab.slab_range(total_batch, world, rank)
     batch = b1 - b0
@@ -412,10 +413,10 @@ def main():
             "metric": "dpotrf_batch_strided n=32 fp64 throughput",
             "value": value, "unit": "matrices/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak",
+            "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"strided dpotrf_batch n=32 lda=32 batch={total_batch} fp64 "
-                                   f"({'BASELINE configs[1] at n=32' if world == 1 else 'BASELINE configs[4], contiguous slabs'})",
+                                   f"({'BASELINE configs[1] at n=32' if world == 1 else 'BASELINE configs[4] layout: 2^20 matrices per GPU, contiguous slabs'})",
                        "batch_total": total_batch, "batch_per_gpu": batch, "n": n, "uplo": "L",
                        "l2_policy": f"inputs larger than L2: {bytes_batch / 2**30:.1f} GiB per step per GPU, a fresh buffer every step",
                        "parallelism": f"batch slab x{world}, no collective"},
