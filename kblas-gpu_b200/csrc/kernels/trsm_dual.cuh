@@ -1,5 +1,6 @@
-// kernels/trsm_dual.cuh -- side-R batched triangular solves / fused POTRS with a full NP x NP factor
-// (NP = 16, 24, 32), TWO right-hand-side vectors per lane and two problems per warp (sm_100a).
+// kernels/trsm_dual.cuh -- batched triangular solves (all four side / trans variants) and the fused POTRS
+// with a full NP x NP factor (NP = 16, 24, 32): TWO right-hand-side vectors per lane and two problems per
+// warp (sm_100a).
 //
 // Why: ncu of the one-vector-per-lane kernel (kernels/trsm_small.cuh) on dpotrs n = 32 shows the
 // shared-memory data pipe 86 % busy (profiles/r01_ncu_dpotrs32_tri_solve_small.json): every broadcast
@@ -11,8 +12,11 @@
 //     addresses of one instruction never share a bank;
 //   * the factor goes global -> shared memory with cp.async (LDGSTS): no staging registers, no STS,
 //     and it is in flight together with the 64 predicated loads of B;
-//   * forward and backward substitution run on the same registers (POTRS = one pass over B).
-// Ragged k, side L and vec > 32 handled by slabs here / by the older kernels in the dispatch.
+//   * forward and backward substitution run on the same registers (POTRS = one pass over B);
+//   * side L (vectors = columns of B): B is read and written coalesced along its rows and transposed
+//     through a padded shared-memory tile per problem, instead of the reference's stride-ldb per-lane
+//     accesses (Xtrsm_batch_kernels.cuh:580-589).
+// vec > 32 is handled by 32-vector slabs; ragged k goes to the older kernels in the dispatch.
 #pragma once
 
 #include "common.cuh"
@@ -28,10 +32,13 @@ __device__ __forceinline__ void lds_vec(float (&v)[4], const float *p) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"((unsigned)__cvta_generic_to_shared(p)));
 }
 
-template <typename T, int NP>
+template <typename T, int NP, bool LEFT = false>
 struct TriDualSmem {
   static constexpr int VW = 16 / (int)sizeof(T);
   static constexpr int per_problem = NP * NP + NP + VW;  // factor + reciprocal diagonal + bank-skew pad
+  static constexpr int tile_stride = NP + 1;             // odd: conflict-free transposed reads
+  static constexpr int tile = LEFT ? 32 * tile_stride + (sizeof(T) == 4 ? 16 : 0) : 0;  // side L: 32 vectors x NP entries (+ bank skew between the two problems, fp32)
+  static constexpr int per_warp = 2 * (per_problem + tile);
   static_assert((per_problem * sizeof(T)) % 16 == 0 && (per_problem * sizeof(T)) % 128 != 0,
                 "the two factor copies of a warp must sit a non-zero multiple of 16 B apart (mod 128)");
 };
@@ -45,8 +52,8 @@ struct TriDualSmem {
 #ifndef KX_DUAL_FENCE32
 #define KX_DUAL_FENCE32 4
 #endif
-template <typename T, int NP, int OP, int WARPS, bool STRIDED>
-__global__ void __launch_bounds__(WARPS * 32, sizeof(T) == 8 ? KX_DUAL_MINB64 : (NP > 24 ? 3 : 4))
+template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED>
+__global__ void __launch_bounds__(WARPS * 32, (sizeof(T) == 8 ? KX_DUAL_MINB64 : (NP > 24 ? 3 : 4)) * 4 / WARPS)
 tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda, BatchRef<T, STRIDED> Bref,
                       const int ldb, const int batchCount, const int slabs) {
   constexpr int VW = 16 / (int)sizeof(T);
@@ -58,8 +65,10 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = lane >> 4, lg = lane & 15;
-  T *Ls = reinterpret_cast<T *>(smem_raw) + (warp * 2 + g) * FSZ;
+  T *Ls = reinterpret_cast<T *>(smem_raw) + warp * TriDualSmem<T, NP, LEFT>::per_warp + g * FSZ;
   T *invd = Ls + NP * NP;
+  constexpr int TS = TriDualSmem<T, NP, LEFT>::tile_stride;
+  T *tile = reinterpret_cast<T *>(smem_raw) + warp * TriDualSmem<T, NP, LEFT>::per_warp + 2 * FSZ + g * TriDualSmem<T, NP, LEFT>::tile;
 
   const long ntask = (long)batchCount * slabs;
   const long task = ((long)blockIdx.x * WARPS + warp) * 2 + g;  // (matrix, 32-vector slab)
@@ -78,16 +87,46 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
       const int r = lg + 16 * hh;
       if (16 * hh < NP) cp_async_elem(Ls + r + c * NP, A + r + (long)c * lda, r < NP && ((r | (SE - 1)) >= c));
     }
-  // ---- my two rows of B (vectors v0 + lg and v0 + lg + 16), all loads in flight --------------------------
+  // ---- my two vectors (v0 + lg and v0 + lg + 16) ------------------------------------------------------------
   T x0[NP], x1[NP];
   const int my0 = v0 + lg, my1 = v0 + lg + 16;
   const bool h0 = live && my0 < vec, h1 = live && my1 < vec;
+  if (!LEFT) {
+    // side R: vector = row of B; all 2 NP loads in flight
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    x0[j] = T(0);
-    x1[j] = T(0);
-    ldg_stream_if(x0[j], B + my0 + (long)j * ldb, h0);
-    ldg_stream_if(x1[j], B + my1 + (long)j * ldb, h1);
+    for (int j = 0; j < NP; ++j) {
+      x0[j] = T(0);
+      x1[j] = T(0);
+      ldg_stream_if(x0[j], B + my0 + (long)j * ldb, h0);
+      ldg_stream_if(x1[j], B + my1 + (long)j * ldb, h1);
+    }
+  } else {
+    // side L: vector = column of B.  Lane lg reads rows lg and lg+16 of 16 columns at a time (coalesced) and
+    // parks them in the tile as tile[column][row]; the vectors are then read back along the rows.
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      T t0[16], t1[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const bool hc = live && (v0 + c0 + c) < vec;
+        t0[c] = T(0);
+        t1[c] = T(0);
+        ldg_stream_if(t0[c], B + lg + (long)(v0 + c0 + c) * ldb, hc);
+        ldg_stream_if(t1[c], B + lg + 16 + (long)(v0 + c0 + c) * ldb, hc && (lg + 16 < NP));
+      }
+      sched_fence();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        tile[(c0 + c) * TS + lg] = t0[c];
+        if (NP > 16 && lg + 16 < NP) tile[(c0 + c) * TS + lg + 16] = t1[c];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      x0[j] = tile[lg * TS + j];
+      x1[j] = tile[(lg + 16) * TS + j];
+    }
   }
   cp_async_wait_all();
   __syncwarp();
@@ -152,10 +191,35 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
   }
 
   T *Bs = launder(B);  // fresh addresses for the stores (see launder)
+  if (!LEFT) {
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    stg_stream_if(Bs + my0 + (long)j * ldb, x0[j], h0);
-    stg_stream_if(Bs + my1 + (long)j * ldb, x1[j], h1);
+    for (int j = 0; j < NP; ++j) {
+      stg_stream_if(Bs + my0 + (long)j * ldb, x0[j], h0);
+      stg_stream_if(Bs + my1 + (long)j * ldb, x1[j], h1);
+    }
+  } else {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      tile[lg * TS + j] = x0[j];
+      tile[(lg + 16) * TS + j] = x1[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      T t0[16], t1[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        t0[c] = tile[(c0 + c) * TS + lg];
+        t1[c] = (NP > 16 && lg + 16 < NP) ? tile[(c0 + c) * TS + lg + 16] : T(0);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const bool hc = live && (v0 + c0 + c) < vec;
+        stg_stream_if(Bs + lg + (long)(v0 + c0 + c) * ldb, t0[c], hc);
+        stg_stream_if(Bs + lg + 16 + (long)(v0 + c0 + c) * ldb, t1[c], hc && (lg + 16 < NP));
+      }
+    }
   }
 }
 

@@ -35,16 +35,16 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
   return KBLAS_Success;
 }
 
-// side R, full NP x NP factor: two vectors per lane, two problems per warp, cp.async staging (kernels/trsm_dual.cuh)
-template <typename T, int NP, int OP, bool STRIDED>
+// full NP x NP factor: two vectors per lane, two problems per warp, cp.async staging (kernels/trsm_dual.cuh)
+template <typename T, int NP, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                            BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  constexpr int WARPS = 4;
+  constexpr int WARPS = LEFT ? 2 : 4;  // side L carries a transpose tile per problem: 2-warp CTAs keep 3 CTAs per SM
   const int slabs = (vec + 31) / 32;
   const long tasks = (long)batchCount * slabs;
   const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
-  const size_t smem = (size_t)WARPS * 2 * TriDualSmem<T, NP>::per_problem * sizeof(T);
-  auto kern = tri_solve_dual_kernel<T, NP, OP, WARPS, STRIDED>;
+  const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
+  auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
@@ -150,12 +150,13 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
     if (k <= 8 && vec <= 16) return launch_tri_bcast<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 16 && vec <= 16) return launch_tri_bcast<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
   }
-  if constexpr (!LEFT) {
-    if (h->variant_override != 9 && h->variant_override != 8) {
-      if (k == 16 && vec > 16) return launch_tri_dual<T, 16, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
-      if (k == 24) return launch_tri_dual<T, 24, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
-      if (k == 32) return launch_tri_dual<T, 32, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
-    }
+  // measured (B200, 2^20 problems, side L): dual vs one-vector kernel  fp64 k=32 4.7-5.1 vs 5.1-5.4 ms, k=24 3.0-3.4 vs
+  // 3.6-3.9; fp32 k=24 2.07 vs 2.35 but k=32 2.96-3.07 vs 2.77-2.83 -> fp32 k=32 side L stays on the older kernel
+  const bool dual_ok = !LEFT || !(sizeof(T) == 4 && k == 32);
+  if (h->variant_override != 9 && h->variant_override != 8 && dual_ok && (!LEFT || h->variant_override != 5)) {  // 5 = side L on the older kernel
+    if (k == 16 && vec > 16) return launch_tri_dual<T, 16, LEFT, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
+    if (k == 24) return launch_tri_dual<T, 24, LEFT, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
+    if (k == 32) return launch_tri_dual<T, 32, LEFT, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
   }
   // 8 = the register/shuffle kernel (A/B comparisons)
   if (h->variant_override != 9 && (h->variant_override == 6 || !(sizeof(T) == 4 && !LEFT && k > 8))) {
