@@ -63,23 +63,24 @@ def main():
                 perm = torch.randperm(b, device="cuda")
                 pa = (A.data_ptr() + perm * (n * n * es)).contiguous()
                 pb = (B.data_ptr() + perm * (m * n * es)).contiguous()
-                h = kb.Handle()
-                h.posv_batch_wsquery("R", m, n, b)
-                h.allocate_workspace()
-
                 def restore():
                     A.copy_(P)
                     B.copy_(B0)
                 flops = n ** 3 / 3 + n ** 2 / 2 + n / 6 + 2 * m * n * n
                 algo = (n * (n + 1) + 2 * m * n) * es
-                for name, fn in (("posv_ptr", lambda: h.posv_batch("R", "L", m, n, pa, n, pb, m, b, None, prec=prec)),
-                                 ("potrf_ptr", lambda: h.potrf_batch("L", n, pa, n, b, None, prec=prec))):
-                    best, mean = timeit(fn, restore, reps=3)
-                    fl = flops if name == "posv_ptr" else n ** 3 / 3 + n ** 2 / 2 + n / 6
-                    print(json.dumps({"op": f"{prec}{name}", "n": n, "m": m, "batch": b, "kernel": h.last_kernel,
-                                      "ms_best": best, "Mprob_s": b / best / 1e3, "TFLOPs": b * fl / best / 1e9,
-                                      "algo_GBs": b * algo / best / 1e6, "frac_hbm": b * algo / best / 1e6 / PEAK}), flush=True)
-                h.destroy()
+                for v in variants:
+                    os.environ["KBLAS_B200_VARIANT"] = str(v)
+                    h = kb.Handle()
+                    h.posv_batch_wsquery("R", m, n, b)
+                    h.allocate_workspace()
+                    for name, fn in (("posv_ptr", lambda: h.posv_batch("R", "L", m, n, pa, n, pb, m, b, None, prec=prec)),
+                                     ("potrf_ptr", lambda: h.potrf_batch("L", n, pa, n, b, None, prec=prec))):
+                        best, mean = timeit(fn, restore, reps=3)
+                        fl = flops if name == "posv_ptr" else n ** 3 / 3 + n ** 2 / 2 + n / 6
+                        print(json.dumps({"op": f"{prec}{name}", "n": n, "m": m, "batch": b, "variant": v, "kernel": h.last_kernel,
+                                          "ms_best": best, "Mprob_s": b / best / 1e3, "TFLOPs": b * fl / best / 1e9,
+                                          "algo_GBs": b * algo / best / 1e6, "frac_hbm": b * algo / best / 1e6 / PEAK}), flush=True)
+                    h.destroy()
                 del P, A, B0, B
     else:
         ns = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 16, 8]
