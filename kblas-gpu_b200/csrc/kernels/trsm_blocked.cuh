@@ -43,6 +43,19 @@ __device__ __forceinline__ void stage_tile(T *Ts, const T *__restrict__ A, int l
   __syncwarp();
 }
 
+// L2 prefetch of the 32 x 32 block at (r0, c0) of a k x k factor (hint only; coordinates clamped into the matrix)
+template <typename T>
+__device__ __forceinline__ void prefetch_tile_l2(const T *__restrict__ A, int lda, int k, int r0, int c0, int lane) {
+  constexpr int LPC = (32 * (int)sizeof(T)) / 128 > 0 ? (32 * (int)sizeof(T)) / 128 : 1;  // 128-byte lines per column segment
+#pragma unroll
+  for (int l = lane; l < 32 * LPC; l += 32) {
+    int r = r0 + (l % LPC) * (128 / (int)sizeof(T)), c = c0 + l / LPC;
+    r = r < k ? r : k - 1;
+    c = c < k ? c : k - 1;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + r + (long)c * lda));
+  }
+}
+
 // GP = lanes per matrix: 32 (one matrix per warp, vec may span several 32-vector slabs) or 16 / 8
 // (vec <= GP right-hand sides: 2 / 4 matrices per warp, each lane group with its own staged tiles --
 // posv with 16 right-hand-side rows otherwise leaves half of every warp idle).
@@ -84,6 +97,15 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
         ldg_stream_if(nx[kk], B + b_index<LEFT>(my, k0 + kk, ldb), have && kk < kb);
       }
       __syncwarp();  // previous users of S are done
+      {
+        // pull the block that is needed next into L2 while this one is staged and used (the solve is a chain of
+        // dependent block steps: without the hint each one starts with a DRAM / far-L2 round trip)
+        const bool more = bk + 1 < bi;
+        const int kn = FORWARD ? (K + 1) * NB : (K - 1) * NB;
+        const int pr = FORWARD ? j0 : (more ? kn : j0), pc = FORWARD ? (more ? kn : j0) : j0;
+#pragma unroll
+        for (int q = 0; q < MPW; ++q) prefetch_tile_l2<T>(Aq[q], lda, k, pr, pc, lane);
+      }
       if (FORWARD) {
         // coefficient of x_K[kk] in equation c: L[j0 + c][k0 + kk] = Ts[kk*NB + c]  (axpy form)
 #pragma unroll

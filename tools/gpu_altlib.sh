@@ -5,5 +5,5 @@ cp libkblas-gpu.so libkblas-gpu-base.so
 for v in base $@; do
   cp libkblas-gpu-$v.so libkblas-gpu.so
   echo "== build $v"
-  (cd ../..; python tools/bench_variants.py -1 large 2>/dev/null | python tools/_pv2.py | grep -E "potrf")
+  (cd ../..; python tools/bench_variants.py -1 large 2>/dev/null | python tools/_pv2.py | grep -E "posv")
 done
