@@ -393,7 +393,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_matrix": ALGO_BYTES,
                 "matrices_per_launch": batch, "kernel": impl.kernel_name(), "kernel_ms_mean": kernel_ms,
-                "kernel_ms_min": min(per_step_ms)}
+                "kernel_ms_min": min(per_step_ms), "kernel_ms_median": statistics.median(per_step_ms),
+                "frac_best_step": ALGO_BYTES * batch / (min(per_step_ms) * 1e-3) / 1e9 / peak,   # peak is a best-of-10 (burst) figure too
+                "kernel_ms_steps": [round(x, 3) for x in per_step_ms]}
 
     # ---- e2e: the same call with host (pinned) buffers, copies inside the timed region ---------------
     e2e = None
