@@ -37,7 +37,7 @@ def main():
                 algo = n * (n + 1) * es
                 print(json.dumps({"impl": "reference", "op": f"{prec}potrf", "n": n, "ms_best": best, "Mmat_s": batch / best / 1e3,
                                   "frac": batch * algo / best / 1e6 / PEAK}), flush=True)
-                if n in (32, 16, 8):
+                if n in (32, 24, 16, 8):
                     L = Pm.clone()
                     potrf(ref.h, b"L", n, L.data_ptr(), n, n * n, batch, None)
                     B0 = torch.rand((batch, n, m), device="cuda", dtype=dt)

@@ -83,7 +83,7 @@ def main():
                     h.destroy()
                 del P, A, B0, B
     else:
-        ns = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 16, 8]
+        ns = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 24, 16, 8]
         for prec, dt, es in (("D", torch.float64, 8), ("S", torch.float32, 4)):
             for n in ns:
                 m = n
