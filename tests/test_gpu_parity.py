@@ -219,7 +219,8 @@ def test_potrf_host_pipeline(env, p, n, lda, extra, mode, monkeypatch):
 # trsm / potrs / posv
 @pytest.mark.parametrize("p", ["D", "S"])
 @pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
-@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (32, 32), (13, 7), (7, 13), (32, 20), (20, 32), (1, 1), (24, 24), (32, 100), (100, 32)])
+@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (32, 32), (13, 7), (7, 13), (32, 20), (20, 32), (1, 1), (24, 24), (32, 100), (100, 32),
+                                 (32, 16), (16, 32), (70, 16), (16, 70), (24, 50), (50, 24)])
 def test_trsm_strided_vs_oracle(env, p, side, trans, m, n):
     kb, h, torch = env
     dt = DT[p]
@@ -309,6 +310,54 @@ def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout, monkeypat
     h.destroy()
 
 
+def test_trsm_potrs_random_shapes(env):
+    """seeded sweep over ragged shapes / leading dimensions / both precisions: every dispatch branch of the k <= 32
+    solves (register, broadcast, packed, dual, one-vector kernels) and the blocked kernel for a few k > 32"""
+    kb, h, torch = env
+    rng = np.random.default_rng(2026)
+    seen = set()
+    for it in range(120):
+        p = "DS"[it % 2]
+        dt = DT[p]
+        side, trans = [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")][rng.integers(4)]
+        k = int(rng.choice([1, 2, 5, 8, 9, 12, 16, 17, 23, 24, 29, 32, 33, 48, 64]))
+        vec = int(rng.choice([1, 3, 8, 15, 16, 17, 32, 33, 47]))
+        m, n = (k, vec) if side == "L" else (vec, k)
+        lda, ldb = k + int(rng.integers(0, 3)), m + int(rng.integers(0, 3))
+        batch, alpha = int(rng.integers(1, 40)), float(rng.choice([1.0, 0.28, -2.5]))
+        A = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=it)
+        B0 = U.rand_batch(batch, m, n, ld=ldb, dtype=dt, seed=1000 + it)
+        # factor on the CPU (LAPACK-grade lower factor), solve on the GPU
+        Lf = A.copy()
+        U.oracle_potrf(Lf, k)
+        Bo = B0.copy()
+        U.oracle_trsm(side, "L", trans, "N", m, n, alpha, Lf, Bo)
+        dA, dB = _dev(torch, Lf), _dev(torch, B0)
+        h.trsm_batch_strided_wsquery(side, m, n, batch)
+        h.allocate_workspace()
+        rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, alpha, dA, lda, k * lda, dB, ldb, n * ldb, batch)
+        torch.cuda.synchronize()
+        assert rc == kb.KBLAS_Success, (it, side, trans, m, n)
+        seen.add(h.last_kernel.split("<")[0])
+        got = dB.cpu().numpy()
+        scale = max(1.0, np.abs(Bo[:, :, :m]).max())
+        assert np.abs(got[:, :, :m] - Bo[:, :, :m]).max() <= 100 * k * U.EPS[dt] * scale, (it, p, side, trans, m, n, lda, ldb, h.last_kernel)
+        assert np.array_equal(got[:, :, m:], B0[:, :, m:]), "ldb padding untouched"
+        if side == "R":
+            # potrs on the same factor
+            Bp = B0.copy()
+            U.oracle_potrs("R", "L", m, n, Lf, Bp)
+            dB2 = _dev(torch, B0)
+            h.potrs_batch_strided_wsquery(m, n, batch)
+            h.allocate_workspace()
+            assert h.potrs_batch_strided("R", "L", m, n, dA, lda, k * lda, dB2, ldb, n * ldb, batch) == kb.KBLAS_Success
+            torch.cuda.synchronize()
+            g2 = dB2.cpu().numpy()
+            assert np.abs(g2[:, :, :m] - Bp[:, :, :m]).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bp[:, :, :m]).max()), (it, p, m, n, h.last_kernel)
+            seen.add(h.last_kernel.split("<")[0])
+    assert {"tri_reg", "tri_dual", "tri_small", "tri_blocked"} <= seen, seen
+
+
 def test_trsm_potrs_posv_return_codes(env):
     kb, h, torch = env
     dA, dB = _dev(torch, U.rand_spd_batch(2, 8)), _dev(torch, U.rand_batch(2, 8, 8))
@@ -321,7 +370,7 @@ def test_trsm_potrs_posv_return_codes(env):
 
 
 @pytest.mark.parametrize("p", ["D", "S"])
-@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (24, 24), (32, 32), (16, 32), (5, 13), (40, 32), (3, 1)])
+@pytest.mark.parametrize("m,n", [(8, 8), (16, 16), (24, 24), (32, 32), (16, 32), (5, 13), (40, 32), (3, 1), (32, 16), (70, 16), (50, 24), (100, 8)])
 def test_potrs_and_posv_strided_vs_oracle(env, p, m, n):
     kb, h, torch = env
     dt = DT[p]
