@@ -528,10 +528,11 @@ def run_e2e(torch, dist, impl, n, batch, total_batch, pristine, rank, steps=3, w
     Am = h_in[:1024].cuda().transpose(1, 2)
     res = ((Am - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
     ok = res <= 10 * n * 2.220446049250313e-16
-    nbytes = int(batch * elems * ELEM * tri_frac)
+    nbytes = int(total_batch * elems * ELEM * tri_frac)   # whole job (all ranks), like `value`
     return {"value": total_batch * steps / (ms * 1e-3), "unit": "matrices/s", "h2d_bytes_per_step": nbytes,
-            "d2h_bytes_per_step": nbytes, "steps": steps, "ms_per_step": ms / steps, "wall_s": wall,
-            "host_buffer_bytes_per_step": batch * elems * ELEM, "pipeline": pipeline, "residual_ok": bool(ok)}
+            "d2h_bytes_per_step": nbytes, "bytes_per_step_per_gpu": int(batch * elems * ELEM * tri_frac),
+            "steps": steps, "ms_per_step": ms / steps, "wall_s": wall,
+            "host_buffer_bytes_per_step": total_batch * elems * ELEM, "pipeline": pipeline, "residual_ok": bool(ok)}
 
 
 if __name__ == "__main__":
