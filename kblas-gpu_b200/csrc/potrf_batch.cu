@@ -104,11 +104,11 @@ static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<
 
 // n > 32, default: same panel algorithm with the update on the mma.sync tensor path -- DMMA for fp64,
 // 3 x TF32 for fp32 (kernels/potrf_panel_mma.cuh)
-template <typename T, int THREADS, bool STRIDED>
+template <typename T, int THREADS, bool STRIDED, bool TMA = false>
 static int launch_potrf_panel_mma(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
                                   int *info) {
-  auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED>;
-  const size_t smem = PanelMmaSmem<T, THREADS>::bytes;
+  auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED, TMA>;
+  const size_t smem = PanelMmaSmem<T, THREADS, TMA>::bytes;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
@@ -132,6 +132,9 @@ static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
   // measured (B200, fp64, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
   // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6.  One warp with the
   // cap lifted to 255 registers (8 resident warps per SM, no spills): 5.5 / 9.5 / 14.6
+  if (v == 10)  // operand chunks staged by TMA bulk copies (experimental: needs n % 32 == 0, aligned columns; else falls back inside)
+    return launch_potrf_panel_mma<T, 32, STRIDED, true>(h, sizeof(T) == 8 ? "potrf_panel_dmma_tma<T=32>" : "potrf_panel_tf32x3_tma<T=32>",
+                                                        n, A, lda, batchCount, info);
   if (v == 12) return KX_PANEL_MMA(64);
   if (v == 13) return KX_PANEL_MMA(128);
   if (v == 14) return KX_PANEL_MMA(256);
