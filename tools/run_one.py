@@ -16,7 +16,9 @@ h = kb.Handle()
 h.posv_batch_wsquery("R", m, n, batch); h.posv_batch_strided_wsquery("R", m, n, batch); h.allocate_workspace()
 for it in range(2):
     A = P.clone()
-    if op == "potrs":
+    if op == "potrf":
+        rc = h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
+    elif op == "potrs":
         h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
         rc = h.potrs_batch_strided("R", "L", m, n, A, n, n * n, B, m, m * n, batch)
     elif op.startswith("trsm_"):
