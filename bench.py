@@ -66,6 +66,25 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        # preferred: NVML in-process (pynvml), one sample every 10 ms from a thread -- nvidia-smi -lms needs ~1 s to
+        # come up on a fresh box and then delivers only ~10 samples/s, so a short timed region could end up with none
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml, self.nvml_h, self.stop_flag = pynvml, h, False
+            self.t = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
@@ -79,11 +98,39 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def _pump_nvml(self):
+        nv, h = self.nvml, self.nvml_h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                flags = ["Active" if r & m else "Not Active" for m in (0x8, 0x40, 0x20, 0x4)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                self.rows.append((time.time(), f"{self.gpu}, {mhz}, {mx}, {pw}, {r:#x}, " + ", ".join(flags)))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def stop(self, t0, t1):
-        if not self.proc:
+        if getattr(self, "nvml", None):
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
+        else:
+            deadline = time.time() + 2.0
+            while not self.rows and time.time() < deadline:   # nvidia-smi still starting up: wait for one sample
+                time.sleep(0.05)
+            time.sleep(0.12)
+            self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
@@ -105,8 +152,10 @@ class ClockSampler:
                         reasons.add(name)
         if not sm:  # region shorter than the sampling period: use everything we saw
             sm = [float(l.split(",")[1]) for _, l in self.rows if len(l.split(",")) >= 9] or [0.0]
+        pw = [x for x in pw if x == x]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "source": "nvml" if getattr(self, "nvml", None) else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -138,14 +138,12 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
   // few right-hand sides and a small factor: register kernel, 4 / 2 problems per warp
   // (measured: the shared-memory packed kernel stays ahead only for fp32, side R, 8 < k <= 16)
   // Full 8 / 16 columns with 16-byte aligned columns can read the factor as L1-broadcast vector loads
-  // (kernels/trsm_bcast.cuh; pointer-array entries are checked in the kernel).  Measured on B200 (batch 2^20):
-  // it wins where the register/shuffle kernel runs out of registers -- fp64 potrs k = 16: 1.58 vs 2.74 ms --
-  // and loses by 3-10 % elsewhere (the shuffle kernel at <= 80 registers: dtrsm R k=16 1.03-1.06 ms), so
-  // that is the only case it takes by default; variant 7 forces it everywhere.
+  // (kernels/trsm_bcast.cuh; pointer-array entries are checked in the kernel).  Measured on B200 (batch 2^20) it
+  // loses by 3-10 % to the shuffle kernel at <= 80 registers and, for fp64 potrs k = 16 (1.6 ms), to the dual
+  // kernel (1.07 ms): it is kept as variant 7 only.
   bool vec_ok = (k == 8 || k == 16) && ((size_t)lda * sizeof(T)) % 16 == 0;
   if constexpr (STRIDED) vec_ok = vec_ok && (reinterpret_cast<size_t>(A.base) % 16 == 0) && ((size_t)A.stride * sizeof(T)) % 16 == 0;
-  const bool bcast_default = (OP == TRI_BOTH) && sizeof(T) == 8 && k == 16;
-  if (vec_ok && h->variant_override != 9 && h->variant_override != 8 && (bcast_default || h->variant_override == 7)) {
+  if (vec_ok && h->variant_override == 7) {
     if (k <= 8 && vec <= 8) return launch_tri_bcast<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 8 && vec <= 16) return launch_tri_bcast<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
     if (k <= 16 && vec <= 16) return launch_tri_bcast<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_bcast<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
@@ -154,7 +152,11 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
   // 3.6-3.9; fp32 k=24 2.07 vs 2.35 but k=32 2.96-3.07 vs 2.77-2.83 -> fp32 k=32 side L stays on the older kernel
   const bool dual_ok = !LEFT || !(sizeof(T) == 4 && k == 32);
   if (h->variant_override != 9 && h->variant_override != 8 && dual_ok && (!LEFT || h->variant_override != 5)) {  // 5 = side L on the older kernel
-    if (k == 16 && vec > 16) return launch_tri_dual<T, 16, LEFT, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
+    // k = 16 with <= 16 vectors leaves the second vector of every lane idle and still wins on side R (measured, ms per
+    // 2^20: fp64 potrs 1.07 vs 1.6-2.7, trsm R 0.95 vs 1.01-1.08; fp32 trsm R 0.57-0.59 vs 0.58-0.64); side L and fp32
+    // potrs stay on the register / packed kernels (dual: 1.4-1.5 vs 1.13-1.2; 0.76 vs 0.73)
+    const bool dual16 = vec > 16 || (!LEFT && (sizeof(T) == 8 || OP != TRI_BOTH));
+    if (k == 16 && dual16) return launch_tri_dual<T, 16, LEFT, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
     if (k == 24) return launch_tri_dual<T, 24, LEFT, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
     if (k == 32) return launch_tri_dual<T, 32, LEFT, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
   }
