@@ -109,10 +109,13 @@ static int launch_potrf_panel_mma(KBlasHandle *h, const char *name, int n, Batch
                                   int *info) {
   auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED, TMA>;
   const size_t smem = PanelMmaSmem<T, THREADS, TMA>::bytes;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // per instantiation AND per device: the attribute belongs to the device's context (one process may drive
+  // several GPUs, one handle each, as the reference harness does)
+  static bool attr_set[64] = {};
+  const int dev = (h->device_id >= 0 && h->device_id < 64) ? h->device_id : 0;
+  if (!attr_set[dev]) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<(unsigned)batchCount, THREADS, smem, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
   h->note_launch(name);

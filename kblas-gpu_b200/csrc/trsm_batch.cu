@@ -23,11 +23,14 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
   const long grid = (tasks + WARPS - 1) / WARPS;
   const size_t smem = (size_t)WARPS * TriSmem<NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_small_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // per instantiation AND per device: the attribute belongs to the device's context (one process may drive
+  // several GPUs, one handle each, as the reference harness does)
+  static bool attr_set[64] = {};
+  const int dev = (h->device_id >= 0 && h->device_id < 64) ? h->device_id : 0;
+  if (!attr_set[dev]) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                     KBLAS_CUDA_Error);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
@@ -45,10 +48,13 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
   const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // per instantiation AND per device: the attribute belongs to the device's context (one process may drive
+  // several GPUs, one handle each, as the reference harness does)
+  static bool attr_set[64] = {};
+  const int dev = (h->device_id >= 0 && h->device_id < 64) ? h->device_id : 0;
+  if (!attr_set[dev]) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
@@ -111,10 +117,13 @@ static int launch_tri_blocked_gp(KBlasHandle *h, const char *name, int k, int ve
   const long grid = (tasks + WARPS - 1) / WARPS;
   auto kern = tri_solve_blocked_kernel<T, LEFT, OP, GP, WARPS, STRIDED>;
   const size_t smem = per_warp * WARPS;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // per instantiation AND per device: the attribute belongs to the device's context (one process may drive
+  // several GPUs, one handle each, as the reference harness does)
+  static bool attr_set[64] = {};
+  const int dev = (h->device_id >= 0 && h->device_id < 64) ? h->device_id : 0;
+  if (!attr_set[dev]) {
     check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
