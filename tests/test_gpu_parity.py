@@ -603,3 +603,38 @@ def test_multi_stream_and_timer(env):
     U.oracle_potrf(Lo, n)
     _check_potrf(A0, dA.cpu().numpy(), n, np.float64, Lref=Lo)
     h.set_stream(0)
+
+
+def test_two_devices_one_process(env):
+    """one handle per device from ONE process (what the reference harness does with --ngpu, test_Xpotrf_batch.cpp:97-160):
+    kernels that need a raised dynamic shared-memory limit must work on every device, not only the first."""
+    kb, _, torch = env
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, m, batch = 32, 32, 257
+    A0 = U.rand_spd_batch(batch, n, seed=3)
+    B0 = U.rand_batch(batch, m, n, seed=4)
+    Ao, Bo = A0.copy(), B0.copy()
+    U.oracle_posv("R", "L", m, n, Ao, Bo)
+    try:
+        for dev in (0, 1):
+            torch.cuda.set_device(dev)
+            h = kb.Handle()
+            dA, dB = torch.from_numpy(A0).cuda(dev), torch.from_numpy(B0).cuda(dev)
+            h.posv_batch_strided_wsquery("R", m, n, batch)
+            h.allocate_workspace()
+            assert h.posv_batch_strided("R", "L", m, n, dA, n, n * n, dB, m, m * n, batch, None) == kb.KBLAS_Success
+            torch.cuda.synchronize(dev)
+            assert "tri_dual" in h.last_kernel
+            assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * n * U.EPS[np.float64] * max(1.0, np.abs(Bo).max())
+            # n = 256 potrf: the tensor-path panel kernel also raises its shared-memory limit
+            P = U.rand_spd_batch(9, 256, seed=5)
+            dP = torch.from_numpy(P).cuda(dev)
+            h.potrf_batch_strided_wsquery(256, 9)
+            h.allocate_workspace()
+            assert h.potrf_batch_strided("L", 256, dP, 256, 256 * 256, 9, None) == kb.KBLAS_Success
+            torch.cuda.synchronize(dev)
+            assert U.potrf_residual(P, dP.cpu().numpy(), 256) <= 10 * 256 * U.EPS[np.float64]
+            h.destroy()
+    finally:
+        torch.cuda.set_device(0)
