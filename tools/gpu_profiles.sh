@@ -19,7 +19,7 @@ rm -f gpurun_out/prof_potrf32.ncu-rep
 cap potrs32 tri_solve_dual python tools/run_one.py potrs 32 1048576
 cap trsm32RLT tri_solve_dual python tools/run_one.py trsm_RLT 32 1048576
 cap trsm32LLN tri_solve_dual python tools/run_one.py trsm_LLN 32 1048576
-cap potrs16 tri_solve_bcast python tools/run_one.py potrs 16 1048576
+cap potrs16 tri_solve_dual python tools/run_one.py potrs 16 1048576
 cap potrf256d potrf_panel_mma python tools/run_one.py potrf_ptr 256 16384
 F32=1 cap potrf256s potrf_panel_mma python tools/run_one.py potrf_ptr 256 16384
 cap posv256d tri_solve_blocked python tools/run_one.py posv_ptr 256 16384
