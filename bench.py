@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the batched very-small-matrix Cholesky path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
     torchrun ... bench.py --gpus N ...          (one rank per GPU, N > 1)
 
 Metric (BASELINE.json): strided dpotrf_batch, n = 32, fp64, matrices/s (and GFLOP/s) as a fraction
@@ -20,9 +20,11 @@ host<->device copies inside the timed region.  `roofline` uses the algorithmic b
 MEASURED_PEAKS.json.  `cpu_baseline` is the reference harness's LAPACK dpotrf loop
 (test_Xpotrf_batch.cpp:308-321) on the host cores -- a reported baseline, not the target.
 
---impl reference runs the UNMODIFIED reference GPU library (oracle/_ref/libkblas_ref.so, built from
-/root/reference by oracle/build_ref.sh) through the same harness; if that library cannot be loaded
-it falls back to the reference harness's CPU LAPACK loop (also available as --impl reference-cpu).
+--impl reference is the contract's reference arm: the reference's own CPU implementation of the path -- the
+LAPACK dpotrf loop of its test harness -- on all host cores, each step a bounded sample of the workload
+(rank 0 only under torchrun).  When a GPU and oracle/_ref/libkblas_ref.so are present its line also carries
+`reference_gpu_library`: the UNMODIFIED reference GPU library through this same harness, which is the
+like-for-like comparison (also directly: --impl reference-gpu; falls back to the CPU loop if not loadable).
 """
 from __future__ import annotations
 
@@ -248,6 +250,9 @@ class RefGpuImpl:
 
 
 # ------------------------------------------------------------------------------------------------
+_CPU_PRISTINE = {}
+
+
 def cpu_lapack_loop(n, sample, threads_list, runs=3):
     """reference harness CPU check loop (test_Xpotrf_batch.cpp:308-321) on a bounded sample"""
     import numpy as np
@@ -263,7 +268,10 @@ def cpu_lapack_loop(n, sample, threads_list, runs=3):
     loop.lapack_potrf_loop.restype = C.c_double
     loop.lapack_potrf_loop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_long, C.c_long, C.c_int,
                                        C.POINTER(C.c_long)]
-    pristine = U.rand_spd_batch(sample, n, dtype=np.float64, seed=1)
+    key = (sample, n)
+    if key not in _CPU_PRISTINE:   # generated once per process: the timed loop below only copies it
+        _CPU_PRISTINE[key] = U.rand_spd_batch(sample, n, dtype=np.float64, seed=1)
+    pristine = _CPU_PRISTINE[key]
     out = {}
     for th in threads_list:
         best = None
@@ -293,7 +301,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "reference-cpu"])
     ap.add_argument("--batch", type=int, default=0, help="override the total batch (default 2^20 at N=1, 2^23 at N>1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -307,7 +315,7 @@ def main():
     n = N_MAT
 
     # ---- CPU-only reference arm ---------------------------------------------------------------------
-    if args.impl == "reference-cpu":
+    if args.impl in ("reference", "reference-cpu"):
         if rank != 0:
             return
         sample = 1 << 18
@@ -319,14 +327,34 @@ def main():
         for _ in range(K):
             vals.append(cpu_lapack_loop(n, sample, [cores], runs=1)[cores])
         v = len(vals) * sample / sum(sample / x for x in vals)
+        nper = 1 << 20
         line = {"impl": "reference", "metric": "dpotrf_batch_strided n=32 fp64 throughput", "value": v, "unit": "matrices/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * sample / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"reference harness CPU LAPACK dpotrf loop, n=32 fp64, sample {sample} matrices/step"},
+                "config": {"workload": f"strided dpotrf_batch n=32 lda=32 batch={max(args.gpus, 1) * nper} fp64 "
+                                       f"({'BASELINE configs[1] at n=32' if args.gpus <= 1 else 'BASELINE configs[4] layout'}); "
+                                       f"each step = a bounded sample of {sample} matrices",
+                           "reference_path": "the reference's only CPU implementation of this path: the LAPACK dpotrf loop of its test "
+                                             "harness (testing/batch_triangular/test_Xpotrf_batch.cpp:308-321), restated in "
+                                             "oracle/lapack_loop.c over scipy's OpenBLAS, OpenMP over matrices, all host threads"},
                 "cpu_baseline": {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
-                                 "sample": f"{sample} matrices per step"},
+                                 "sample": f"{sample} random SPD 32x32 fp64 matrices per step (1/4 of the N=1 workload)"},
                 "e2e": {"value": v, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": time.time() - t0}
+        # ride-along (not the arm's value): the unmodified reference GPU library on this box, same harness as our arm
+        if args.impl == "reference" and world == 1 and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libkblas_ref.so")):
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--steps", str(min(K, 10)),
+                                          "--warmup", "3", "--no-cpu"], capture_output=True, text=True, timeout=600)
+                    g = json.loads(out.stdout.strip().splitlines()[-1])
+                    line["reference_gpu_library"] = {
+                        "what": "oracle/_ref/libkblas_ref.so (unmodified reference sources) through bench.py --impl reference-gpu, N=1",
+                        "value": g["value"], "unit": g["unit"], "ms_per_step": g["ms_per_step"],
+                        "roofline_frac": g["roofline"]["frac"], "e2e_value": (g.get("e2e") or {}).get("value")}
+            except Exception as e:   # the ride-along must never break the arm
+                line["reference_gpu_library"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))
         return
 
@@ -346,7 +374,7 @@ def main():
     batch = b1 - b0
 
     impl = None
-    if args.impl == "reference":
+    if args.impl == "reference-gpu":
         try:
             impl = RefGpuImpl()
         except Exception as e:  # library missing / not loadable on this box
@@ -476,7 +504,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if args.impl == "reference":
+        if args.impl == "reference-gpu":
             line["impl"] = "reference"
             line["reference_kind"] = "unmodified KBLAS-GPU sources compiled for sm_100 (oracle/_ref/libkblas_ref.so)"
         print(json.dumps(line))

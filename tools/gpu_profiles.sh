@@ -4,7 +4,7 @@
 # condenses them into profiles/.
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; tail -1 gpurun_out/bench_ours.err
-python bench.py --impl reference --steps 10 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+python bench.py --impl reference-gpu --steps 10 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/b_ncu.log 2>&1
 cap() {  # tag, kernel regex, command...
   tag=$1; rx=$2; shift 2
