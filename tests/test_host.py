@@ -156,3 +156,25 @@ def test_product_does_not_touch_the_oracle():
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt, (dirpath, f)
     out = subprocess.check_output(["ldd", U.kblas().LIB_PATH], text=True)
     assert "oracle" not in out and "openblas" not in out and "cublas" not in out
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU reference arm) runs without a GPU and prints ONE JSON line with the
+    contract's keys; its e2e repeats its own value with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(U.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=U.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "matrices/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 1e4
