@@ -362,9 +362,15 @@ def main():
 
     torch.cuda.set_device(local)
     dist = None
+    real_stdout = None
     if world > 1:
         import torch.distributed as dist_
 
+        # NCCL prints its version banner on fd 1 when the communicator comes up; stdout must carry exactly ONE JSON
+        # line, so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -507,7 +513,12 @@ def main():
         if args.impl == "reference-gpu":
             line["impl"] = "reference"
             line["reference_kind"] = "unmodified KBLAS-GPU sources compiled for sm_100 (oracle/_ref/libkblas_ref.so)"
-        print(json.dumps(line))
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            os.dup2(2, 1)   # whatever NCCL says while shutting down goes to stderr again
     if dist:
         dist.barrier()
         dist.destroy_process_group()
