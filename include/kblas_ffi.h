@@ -65,7 +65,21 @@ int kblasSset_pointer_2(float **output_array1, const float *input1, int ld1, lon
 int kblasDset_pointer_2(double **output_array1, const double *input1, int ld1, long batch_offset1,
                         double **output_array2, const double *input2, int ld2, long batch_offset2,
                         long batchCount, void *stream);
+int kblasSset_pointer_3(float **output_array1, const float *input1, int ld1, long batch_offset1,
+                        float **output_array2, const float *input2, int ld2, long batch_offset2,
+                        float **output_array3, const float *input3, int ld3, long batch_offset3,
+                        long batchCount, void *stream);
+int kblasDset_pointer_3(double **output_array1, const double *input1, int ld1, long batch_offset1,
+                        double **output_array2, const double *input2, int ld2, long batch_offset2,
+                        double **output_array3, const double *input3, int ld3, long batch_offset3,
+                        long batchCount, void *stream);
 int kblas_iset_value_1(int *output_array, int input, long batchCount, void *stream);
+/* reference src/kblas_common.cu:351-386: several int arrays filled in one call */
+int kblas_iset_value_2(int *output_array1, int input1, int *output_array2, int input2, long batchCount, void *stream);
+int kblas_iset_value_4(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                       int *output_array4, int input4, long batchCount, void *stream);
+int kblas_iset_value_5(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                       int *output_array4, int input4, int *output_array5, int input5, long batchCount, void *stream);
 
 /* (3) introspection: no reference counterpart */
 /** workspace bytes recorded in the handle: which = 0 requested, 1 allocated, 2 consumed;

@@ -80,6 +80,9 @@ _sig("kblas_potrf_batch_strided_wsquery", None, _H, _i, _i)
 _sig("kblas_potrs_batch_wsquery", None, _H, _i, _i, _i)
 _sig("kblas_potrs_batch_strided_wsquery", None, _H, _i, _i, _i)
 _sig("kblas_iset_value_1", _i, _P, _i, _l, C.c_void_p)
+_sig("kblas_iset_value_2", _i, _P, _i, _P, _i, _l, C.c_void_p)
+_sig("kblas_iset_value_4", _i, _P, _i, _P, _i, _P, _i, _P, _i, _l, C.c_void_p)
+_sig("kblas_iset_value_5", _i, _P, _i, _P, _i, _P, _i, _P, _i, _P, _i, _l, C.c_void_p)
 _sig("kblasx_workspace_state", _i, _H, _i, C.POINTER(C.c_size_t))
 _sig("kblasx_wsquery_bytes", _i, _i, _i, _c, _i, _i, _i, C.POINTER(C.c_size_t))
 _sig("kblasx_launch_count", _l, _H)
@@ -99,6 +102,7 @@ for _p, _t in (("S", C.c_float), ("D", C.c_double)):
     _sig(f"kblas{_p}posv_batch_strided", _i, _H, _c, _c, _i, _i, _P, _i, _l, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}set_pointer_1", _i, _P, _P, _i, _l, _l, C.c_void_p)
     _sig(f"kblas{_p}set_pointer_2", _i, _P, _P, _i, _l, _P, _P, _i, _l, _l, C.c_void_p)
+    _sig(f"kblas{_p}set_pointer_3", _i, _P, _P, _i, _l, _P, _P, _i, _l, _P, _P, _i, _l, _l, C.c_void_p)
 
 
 def _ptr(x):
@@ -294,8 +298,11 @@ class Handle:
 
     # -- compute: matrices in HOST memory (pinned for full speed); no reference counterpart ----
     def potrf_batch_strided_host(self, uplo, n, A_in, A_out, lda, strideA, batch, info=None, prec=None):
-        """chunked H2D / potrf / D2H pipeline; only the lower triangle crosses PCIe (csrc/host_pipeline.cu).
-        A_in / A_out: CPU torch tensors, numpy arrays or raw host addresses; A_out may be A_in."""
+        """chunked H2D / potrf / D2H pipeline with WHOLE-ARRAY copies by default (csrc/host_pipeline.cu; the
+        lower-triangle-only transfer mode KBLAS_B200_HOSTCOPY=tri measured slower and is opt-in).
+        A_in / A_out: CPU torch tensors, numpy arrays or raw host addresses holding at least
+        (batch-1)*strideA + lda*(n-1) + n elements; A_out may be A_in (in place).  Out of place, A_out receives
+        A_in's storage (padding included) with the lower triangles replaced by the factors."""
         f = getattr(_lib, f"kblasx{_prec(A_in, prec)}potrf_batch_strided_host")
         return f(self._h, _ch(uplo), n, _hptr(A_in), _hptr(A_out), lda, strideA, batch, _hptr(info))
 
@@ -322,5 +329,22 @@ class Handle:
         f = getattr(_lib, f"kblas{_prec(base, prec)}set_pointer_1")
         return f(_ptr(out_array), _ptr(base), lda, batch_offset, batch, self.get_stream() or None)
 
+    def set_pointer_2(self, out1, base1, ld1, off1, out2, base2, ld2, off2, batch, prec=None):
+        f = getattr(_lib, f"kblas{_prec(base1, prec)}set_pointer_2")
+        return f(_ptr(out1), _ptr(base1), ld1, off1, _ptr(out2), _ptr(base2), ld2, off2, batch, self.get_stream() or None)
+
+    def set_pointer_3(self, out1, base1, ld1, off1, out2, base2, ld2, off2, out3, base3, ld3, off3, batch, prec=None):
+        f = getattr(_lib, f"kblas{_prec(base1, prec)}set_pointer_3")
+        return f(_ptr(out1), _ptr(base1), ld1, off1, _ptr(out2), _ptr(base2), ld2, off2, _ptr(out3), _ptr(base3), ld3,
+                 off3, batch, self.get_stream() or None)
+
     def iset_value_1(self, out_array, value, batch):
         return _lib.kblas_iset_value_1(_ptr(out_array), value, batch, self.get_stream() or None)
+
+    def iset_values(self, pairs, batch):
+        """iset_value_{1,2,4,5} (reference src/kblas_common.cu:344-386): pairs = [(int32 device array, value), ...]"""
+        f = getattr(_lib, f"kblas_iset_value_{len(pairs)}")
+        flat = []
+        for arr, val in pairs:
+            flat += [_ptr(arr), int(val)]
+        return f(*flat, batch, self.get_stream() or None)

@@ -69,8 +69,29 @@ int kblasDset_pointer_2(double **out1, const double *in1, int ld1, long off1, do
                         int ld2, long off2, long batchCount, void *stream) {
   return kblasx::set_pointer_2<double>(out1, in1, ld1, off1, out2, in2, ld2, off2, batchCount, (cudaStream_t)stream);
 }
+int kblasSset_pointer_3(float **out1, const float *in1, int ld1, long off1, float **out2, const float *in2, int ld2,
+                        long off2, float **out3, const float *in3, int ld3, long off3, long batchCount, void *stream) {
+  return kblasx::set_pointer_3<float>(out1, in1, ld1, off1, out2, in2, ld2, off2, out3, in3, ld3, off3, batchCount,
+                                      (cudaStream_t)stream);
+}
+int kblasDset_pointer_3(double **out1, const double *in1, int ld1, long off1, double **out2, const double *in2,
+                        int ld2, long off2, double **out3, const double *in3, int ld3, long off3, long batchCount,
+                        void *stream) {
+  return kblasx::set_pointer_3<double>(out1, in1, ld1, off1, out2, in2, ld2, off2, out3, in3, ld3, off3, batchCount,
+                                       (cudaStream_t)stream);
+}
 int kblas_iset_value_1(int *output_array, int input, long batchCount, void *stream) {
   return iset_value_1(output_array, input, batchCount, (cudaStream_t)stream);
+}
+int kblas_iset_value_2(int *output_array1, int input1, int *output_array2, int input2, long batchCount, void *stream) {
+  return iset_value_2(output_array1, input1, output_array2, input2, batchCount, (cudaStream_t)stream);
+}
+int kblas_iset_value_4(int *o1, int i1, int *o2, int i2, int *o3, int i3, int *o4, int i4, long batchCount, void *stream) {
+  return iset_value_4(o1, i1, o2, i2, o3, i3, o4, i4, batchCount, (cudaStream_t)stream);
+}
+int kblas_iset_value_5(int *o1, int i1, int *o2, int i2, int *o3, int i3, int *o4, int i4, int *o5, int i5,
+                       long batchCount, void *stream) {
+  return iset_value_5(o1, i1, o2, i2, o3, i3, o4, i4, o5, i5, batchCount, (cudaStream_t)stream);
 }
 
 // ---- introspection (no reference counterpart) ---------------------------------------------

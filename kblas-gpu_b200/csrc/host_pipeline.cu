@@ -16,7 +16,10 @@
 //     caller's bits both ways; in place the result is still bit-identical.)
 //   * zero-copy (the kernel run directly on pinned host memory, tools/zero_copy_test.py): 350 ms.
 // In place (A_out == A_in) the result is bit-identical to cudaMemcpy + kblas_potrf_batch + cudaMemcpy.
+// Out of place, whole-array mode: A_out receives a copy of A_in's storage (padding between columns and between
+// matrices included, up to the last element of the last matrix) with the lower triangles replaced by the factors.
 // Out of place in tri mode, elements of A_out above the diagonal blocks are not written.
+// Host buffers must hold (batchCount-1)*strideA + lda*(n-1) + n elements -- the minimal strided allocation.
 #include <cstdlib>
 
 #include "kblas_common.h"
@@ -90,8 +93,14 @@ void host_pipe_destroy(void *pp) {
 // Copy `count` matrices between a host and a device array of identical (lda, stride) geometry.
 // tri: lower triangle in 8-column groups through strided 3-D copies; otherwise one contiguous copy.
 static cudaError_t copy_matrices(void *dst, const void *src, size_t es, int n, int lda, long stride, long count, bool tri,
-                                 cudaMemcpyKind kind, cudaStream_t s) {
-  if (!tri) return cudaMemcpyAsync(dst, src, (size_t)count * stride * es, kind, s);
+                                 bool last, cudaMemcpyKind kind, cudaStream_t s) {
+  // whole-array mode: count*stride elements, except that the chunk holding the batch's LAST matrix stops at that
+  // matrix's last element ((count-1)*stride + lda*(n-1) + n elements): a caller with stride > lda*n owns no storage
+  // behind it (the usual minimal strided allocation)
+  if (!tri) {
+    const size_t elems = last ? ((size_t)(count - 1) * stride + (size_t)lda * (n - 1) + n) : (size_t)count * stride;
+    return cudaMemcpyAsync(dst, src, elems * es, kind, s);
+  }
   const size_t pitch = (size_t)lda * es;
   const size_t cols_per_matrix = (size_t)(stride / lda);  // tri requires stride % lda == 0
   for (int c0 = 0; c0 < n; c0 += 8) {
@@ -148,7 +157,7 @@ int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T 
     T *d = static_cast<T *>(p->dbuf[b]);
     // H2D once the previous result has left this buffer
     if (c >= HP_NBUF) check_error_ret(cudaStreamWaitEvent(p->s_in, p->ev_out[b], 0), KBLAS_CUDA_Error);
-    check_error_ret(copy_matrices(d, A_in + lo * strideA, sizeof(T), n, lda, strideA, cnt, tri, cudaMemcpyHostToDevice, p->s_in),
+    check_error_ret(copy_matrices(d, A_in + lo * strideA, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyHostToDevice, p->s_in),
                     KBLAS_CUDA_Error);
     check_error_ret(cudaEventRecord(p->ev_in[b], p->s_in), KBLAS_CUDA_Error);
     // factorise on the handle's stream
@@ -161,7 +170,7 @@ int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T 
     check_error_ret(cudaEventRecord(p->ev_k[b], h->stream), KBLAS_CUDA_Error);
     // D2H
     check_error_ret(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0), KBLAS_CUDA_Error);
-    check_error_ret(copy_matrices(A_out + lo * strideA, d, sizeof(T), n, lda, strideA, cnt, tri, cudaMemcpyDeviceToHost, p->s_out),
+    check_error_ret(copy_matrices(A_out + lo * strideA, d, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyDeviceToHost, p->s_out),
                     KBLAS_CUDA_Error);
     if (want_info)
       check_error_ret(cudaMemcpyAsync(info_host + lo, p->dinfo[b], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, p->s_out),

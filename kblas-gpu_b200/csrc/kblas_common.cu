@@ -65,20 +65,54 @@ long kblas_roundup_l(long x, long y) { return long((x + y - 1) / y) * y; }
 size_t kblas_roundup_s(size_t x, size_t y) { return size_t((x + y - 1) / y) * y; }
 
 // ---------------------------------------------------------------------------------------------
-// iset_value_1 (reference src/kblas_common.cu:344-386): output[i] = input
-__global__ void kblasx_iset_value_kernel(int *__restrict__ out, int v, long count) {
+// iset_value_{1,2,4,5} (reference src/kblas_common.cu:344-386): output_k[i] = input_k for K arrays in ONE
+// grid-stride launch (the reference: grid = batchCount/256 blocks per call, one kernel per arity)
+namespace {
+template <int K>
+struct ISetJob {
+  int *out[K];
+  int v[K];
+};
+template <int K>
+__global__ void kblasx_iset_value_kernel(ISetJob<K> job, long count) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long step = (long)gridDim.x * blockDim.x;
-  for (; i < count; i += step) out[i] = v;
+  for (; i < count; i += step) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) job.out[k][i] = job.v[k];
+  }
 }
-
-int iset_value_1(int *output_array, int input, long batchCount, cudaStream_t cuda_stream) {
+template <int K>
+int iset_launch(const ISetJob<K> &job, long batchCount, cudaStream_t s) {
   if (batchCount <= 0) return KBLAS_Success;
   long blocks = (batchCount + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
-  kblasx_iset_value_kernel<<<(unsigned)blocks, 256, 0, cuda_stream>>>(output_array, input, batchCount);
+  kblasx_iset_value_kernel<K><<<(unsigned)blocks, 256, 0, s>>>(job, batchCount);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
+}
+}  // namespace
+
+int iset_value_1(int *output_array, int input, long batchCount, cudaStream_t cuda_stream) {
+  ISetJob<1> j = {{output_array}, {input}};
+  return iset_launch(j, batchCount, cuda_stream);
+}
+int iset_value_2(int *output_array1, int input1, int *output_array2, int input2, long batchCount,
+                 cudaStream_t cuda_stream) {
+  ISetJob<2> j = {{output_array1, output_array2}, {input1, input2}};
+  return iset_launch(j, batchCount, cuda_stream);
+}
+int iset_value_4(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                 int *output_array4, int input4, long batchCount, cudaStream_t cuda_stream) {
+  ISetJob<4> j = {{output_array1, output_array2, output_array3, output_array4}, {input1, input2, input3, input4}};
+  return iset_launch(j, batchCount, cuda_stream);
+}
+int iset_value_5(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                 int *output_array4, int input4, int *output_array5, int input5, long batchCount,
+                 cudaStream_t cuda_stream) {
+  ISetJob<5> j = {{output_array1, output_array2, output_array3, output_array4, output_array5},
+                  {input1, input2, input3, input4, input5}};
+  return iset_launch(j, batchCount, cuda_stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,9 +240,23 @@ KBlasHandle::KBlasHandle(int /*use_magma*/, cudaStream_t stream_, int device_id_
   info_mode = (im && !strcmp(im, "lapack")) ? KBLASX_INFO_LAPACK : KBLASX_INFO_COMPAT;
   const char *vo = getenv("KBLAS_B200_VARIANT");
   variant_override = vo ? atoi(vo) : -1;
+  const char *xs = getenv("KBLAS_B200_ELEMENT_EXACT_STORES");
+  exact_stores = (xs && atoi(xs) != 0) ? 1 : 0;
   launch_count = 0;
   last_kernel = "none";
   host_pipe = NULL;
+  n_kernel_notes = 0;
+}
+
+KBlasHandle::KernelNote *KBlasHandle::kernel_note(const void *fn) {
+  for (int i = 0; i < n_kernel_notes; ++i)
+    if (kernel_notes[i].fn == fn) return &kernel_notes[i];
+  // table full (cannot happen with the kernels of this library): recycle the last slot, costing a re-query
+  KernelNote *k = &kernel_notes[n_kernel_notes < KERNEL_NOTES ? n_kernel_notes++ : KERNEL_NOTES - 1];
+  k->fn = fn;
+  k->ctas_per_sm = 0;
+  k->smem_limit = 0;
+  return k;
 }
 
 // minimal lazily-bound cuBLAS (only for kblasGetCublasHandle / kblasSetStream parity)

@@ -14,6 +14,13 @@ size_t kblas_roundup_s(size_t x, size_t y);
 
 // reference src/kblas_common.h:35-36, src/kblas_common.cu:344-386
 int iset_value_1(int *output_array, int input, long batchCount, cudaStream_t cuda_stream);
+int iset_value_2(int *output_array1, int input1, int *output_array2, int input2, long batchCount,
+                 cudaStream_t cuda_stream);
+int iset_value_4(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                 int *output_array4, int input4, long batchCount, cudaStream_t cuda_stream);
+int iset_value_5(int *output_array1, int input1, int *output_array2, int input2, int *output_array3, int input3,
+                 int *output_array4, int input4, int *output_array5, int input5, long batchCount,
+                 cudaStream_t cuda_stream);
 
 // reference src/kblas_common.cu:208-238: print to stderr, return 1 on success / 0 on error
 int _kblas_error(cudaError_t err, const char *func, const char *file, int line);
@@ -30,6 +37,29 @@ int _kblas_error(int err, const char *func, const char *file, int line);
     int _st = (call_);                                                      \
     if (!_kblas_error(_st, __func__, __FILE__, __LINE__)) return _st;        \
   } while (0)
+
+// ---- launch helpers: per-handle (per-device) caches instead of function-local statics -------------
+// resident CTAs per SM of `kern` at this block size / dynamic shared memory on the handle's device
+template <typename K>
+inline int kx_ctas_per_sm(KBlasHandle *h, K kern, int threads, size_t smem, int fallback) {
+  KBlasHandle::KernelNote *k = h->kernel_note((const void *)kern);
+  if (k->ctas_per_sm == 0) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    k->ctas_per_sm = occ > 0 ? occ : fallback;
+  }
+  return k->ctas_per_sm;
+}
+// raise the dynamic shared-memory limit of `kern` on the CURRENT device (once per handle and size)
+template <typename K>
+inline cudaError_t kx_allow_smem(KBlasHandle *h, K kern, size_t smem) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  KBlasHandle::KernelNote *k = h->kernel_note((const void *)kern);
+  if ((size_t)k->smem_limit >= smem) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) k->smem_limit = (int)smem;
+  return e;
+}
 
 // ---- implementation functions behind both the C++-mangled API (kblas_common.cu,
 //      workspace_queries.cu) and its C-linkage twins (ffi.cu) ---------------------------

@@ -124,9 +124,22 @@ struct KBlasHandle {
   int sm_count;            // multiProcessorCount of device_id
   int info_mode;           // KBlasxInfoMode
   int variant_override;    // -1 = auto; tuning / ablation hook (env KBLAS_B200_VARIANT)
+  int exact_stores;        // env KBLAS_B200_ELEMENT_EXACT_STORES=1: potrf never stores a strict-upper element
   long launch_count;       // kernels launched through this handle
   const char *last_kernel; // name of the last dispatched kernel variant
   void *host_pipe;         // staging buffers / streams of the host-memory entry points (host_pipeline.cu), lazily created
+  // per-handle (= per-device, single-threaded by contract) launch cache, keyed by kernel address: resident CTAs
+  // per SM and "dynamic shared-memory limit raised".  Function-local statics would be shared by every device
+  // and every host thread of the process.
+  struct KernelNote {
+    const void *fn;
+    int ctas_per_sm;   // 0 = not queried yet
+    int smem_limit;    // bytes the MaxDynamicSharedMemorySize attribute was raised to (0 = never)
+  };
+  static const int KERNEL_NOTES = 128;
+  KernelNote kernel_notes[KERNEL_NOTES];
+  int n_kernel_notes;
+  KernelNote *kernel_note(const void *fn);
 
   explicit KBlasHandle(int use_magma, cudaStream_t stream = 0, int device_id = 0);
   ~KBlasHandle();

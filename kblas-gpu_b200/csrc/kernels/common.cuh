@@ -5,6 +5,9 @@
 
 namespace kblasx {
 
+// which substitution a triangular-solve kernel runs (trsm: one of the two; potrs: both, fused)
+enum TriOp { TRI_FORWARD = 0, TRI_BACKWARD = 1, TRI_BOTH = 2 };
+
 template <typename T> struct Vec2T;
 template <> struct Vec2T<double> { typedef double2 type; };
 template <> struct Vec2T<float>  { typedef float2 type; };
@@ -24,8 +27,9 @@ template <typename T> struct BatchRef<T, true> {
 };
 template <typename T> struct BatchRef<T, false> {
   T *const *base;
-  long stride;  // unused
-  __device__ __forceinline__ T *at(long b) const { return base[b]; }
+  long stride;  // pointer-array mode: ELEMENT OFFSET added to every entry (the reference's A_row_off + A_col_off*lda
+                // of Xpotrf_batch_offset & co., Xpotrf_batch.cu:44-48; its drivers launch pointer fix-up kernels instead)
+  __device__ __forceinline__ T *at(long b) const { return base[b] + stride; }
 };
 
 // ---- streaming global access ----------------------------------------------------------

@@ -7,8 +7,7 @@
 //         tests: same tolerances as the FFMA kernel) at 1/3 of the TF32 tensor rate, which is still
 //         several times the FFMA pipe and needs no shared-memory broadcast traffic.
 //
-// Same panel algorithm as kernels/potrf_panel.cuh (the FFMA/DFMA version, kept for A/B comparisons):
-// for the panel of columns j0 .. j0+31 every warp owns a 32-row x 32-column block of the panel.
+// For the panel of columns j0 .. j0+31 every warp owns a 32-row x 32-column block of the panel.
 //   1. update: acc(32x32) = L[rows, 0:j0] * L[j0:j0+32, 0:j0]^T, operands fetched straight from
 //      global/L2 in fragment order: both the A fragment (rows of this warp) and the B fragment
 //      (rows j0.. of the panel) are "element (base + lane/4, k + lane%4)" of the same column-major
@@ -19,7 +18,7 @@
 //   2. the accumulators go through (padded) shared memory into a row-per-thread layout,
 //      p = A[row, j0:j0+32] - acc;
 //   3. warp 0 factors the diagonal block (row per lane), 4. the other rows solve against it,
-//   5. rows are stored -- identical to the FMA kernel.
+//   5. rows are stored.
 // Measured on B200: DMMA peaks at 63.5 FMA/clk/SM, the same as the DFMA pipe
 // (profiles/r01_microbench_pipes.txt); it wins by freeing issue slots and the MIO pipe.
 #pragma once
@@ -51,41 +50,13 @@ __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 
-template <typename T, int THREADS, bool TMA = false>
+template <typename T, int THREADS>
 struct PanelMmaSmem {
   static constexpr int NB = 32;
   static constexpr int LD = 33;  // odd row stride: conflict-free row-per-thread reads
-  static constexpr int RS = 40;  // TMA-staged operand chunk: elements per staged column (32 rows + skew: the 32 lanes
-                                 // of a fragment load hit 32 distinct banks (fp32) / the minimum 2 wavefronts (fp64))
   static constexpr int warps = THREADS / 32;
-  static constexpr size_t base = sizeof(T) * (NB * NB + NB + (size_t)warps * NB * LD);
-  static constexpr size_t stage = TMA ? 2 * NB * RS * sizeof(T) : 0;  // double-buffered 32-column chunk
-  static constexpr size_t bytes = ((base + 15) / 16) * 16 + stage + (TMA ? 16 : 0);  // + two mbarriers
+  static constexpr size_t bytes = sizeof(T) * (NB * NB + NB + (size_t)warps * NB * LD);
 };
-
-// ---- TMA (cp.async.bulk, SASS UBLKCP) staging of the panel's own rows L[j0 : j0+32, k0 : k0+32] ----------
-// One bulk copy per column (32 contiguous rows), issued by lane = column, completion counted on an mbarrier.
-__device__ __forceinline__ void mbar_init(uint32_t bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-template <typename T>
-__device__ __forceinline__ void tma_issue_chunk(const T *__restrict__ A, const int lda, const int j0, const int k0,
-                                                const uint32_t bs, const uint32_t bar, const int lane) {
-  constexpr uint32_t COLB = 32 * sizeof(T);
-  constexpr uint32_t RSB = PanelMmaSmem<T, 32, true>::RS * sizeof(T);
-  if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32 * COLB) : "memory");
-  __syncwarp();
-  const T *src = A + j0 + (long)(k0 + lane) * lda;
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(bs + lane * RSB), "l"(src), "r"(COLB), "r"(bar) : "memory");
-}
 
 // acc_w(32 x LD, row-major) = L[wrow0 .. wrow0+31, 0:j0] * L[j0 .. j0+31, 0:j0]^T   (one warp)
 __device__ __forceinline__ void panel_update_mma(double *acc_w, const int LD, const double *__restrict__ A, const int lda,
@@ -201,127 +172,6 @@ __device__ __forceinline__ void panel_update_mma(float *acc_w, const int LD, con
     }
 }
 
-// Same update with the B operand (the panel's own rows) staged by TMA in 32-column chunks, double buffered:
-// the chunk for step c+1 is in flight while chunk c feeds the MMAs; only the A operand (this slab's rows) is
-// still fetched by the lanes.  Requires n % 32 == 0 and 16-byte aligned columns (checked by the caller).
-__device__ __forceinline__ void panel_update_mma_tma(double *acc_w, const int LD, const double *__restrict__ A, const int lda,
-                                                     const int wrow0, const int j0, const int lane, const double *Bs,
-                                                     const uint32_t bs_addr, const uint32_t bar_addr, uint32_t &ph0, uint32_t &ph1) {
-  constexpr int RS = PanelMmaSmem<double, 32, true>::RS;
-  constexpr uint32_t BUFB = 32 * RS * sizeof(double);
-  const int fr = lane >> 2, fk = lane & 3;
-  double acc[4][4][2];
-#pragma unroll
-  for (int rb = 0; rb < 4; ++rb)
-#pragma unroll
-    for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
-  const int nch = j0 / 32;
-  tma_issue_chunk<double>(A, lda, j0, 0, bs_addr, bar_addr, lane);
-  const double *col = A + (long)fk * lda + wrow0 + fr;
-  for (int c = 0; c < nch; ++c) {
-    const int buf = c & 1;
-    if (c + 1 < nch) tma_issue_chunk<double>(A, lda, j0, 32 * (c + 1), bs_addr + (buf ^ 1) * BUFB, bar_addr + 8 * (buf ^ 1), lane);
-    mbar_wait(bar_addr + 8 * buf, buf ? ph1 : ph0);
-    if (buf) ph1 ^= 1; else ph0 ^= 1;
-    const double *bsb = Bs + buf * 32 * RS + fk * RS + fr;
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        af[b] = col[8 * b];
-        bf[b] = bsb[4 * k4 * RS + 8 * b];
-      }
-#pragma unroll
-      for (int rb = 0; rb < 4; ++rb)
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) dmma_m8n8k4(acc[rb][cb][0], acc[rb][cb][1], af[rb], bf[cb]);
-      col += 4 * (long)lda;
-    }
-    __syncwarp();  // every lane is done with this buffer before the next issue overwrites it
-  }
-#pragma unroll
-  for (int rb = 0; rb < 4; ++rb)
-#pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-      acc_w[(8 * rb + fr) * LD + 8 * cb + 2 * fk] = acc[rb][cb][0];
-      acc_w[(8 * rb + fr) * LD + 8 * cb + 2 * fk + 1] = acc[rb][cb][1];
-    }
-}
-
-__device__ __forceinline__ void panel_update_mma_tma(float *acc_w, const int LD, const float *__restrict__ A, const int lda,
-                                                     const int wrow0, const int j0, const int lane, const float *Bs,
-                                                     const uint32_t bs_addr, const uint32_t bar_addr, uint32_t &ph0, uint32_t &ph1) {
-  constexpr int RS = PanelMmaSmem<float, 32, true>::RS;
-  constexpr uint32_t BUFB = 32 * RS * sizeof(float);
-  const int fr = lane >> 2, fk = lane & 3;
-  float acc[2][4][4];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-  const int nch = j0 / 32;
-  tma_issue_chunk<float>(A, lda, j0, 0, bs_addr, bar_addr, lane);
-  const float *col0 = A + (long)fk * lda + wrow0 + fr;
-  const float *col1 = A + (long)(fk + 4) * lda + wrow0 + fr;
-  for (int c = 0; c < nch; ++c) {
-    const int buf = c & 1;
-    if (c + 1 < nch) tma_issue_chunk<float>(A, lda, j0, 32 * (c + 1), bs_addr + (buf ^ 1) * BUFB, bar_addr + 8 * (buf ^ 1), lane);
-    mbar_wait(bar_addr + 8 * buf, buf ? ph1 : ph0);
-    if (buf) ph1 ^= 1; else ph0 ^= 1;
-    const float *bsb = Bs + buf * 32 * RS + fk * RS + fr;
-#pragma unroll
-    for (int k8 = 0; k8 < 4; ++k8) {
-      float af[4][2], bf[4][2];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        af[b][0] = col0[8 * b];
-        af[b][1] = col1[8 * b];
-        bf[b][0] = bsb[8 * k8 * RS + 8 * b];
-        bf[b][1] = bsb[(8 * k8 + 4) * RS + 8 * b];
-      }
-      unsigned ah[4][2], al[4][2], bh[4][2], bl[4][2];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          split_tf32(af[b][h], ah[b][h], al[b][h]);
-          split_tf32(bf[b][h], bh[b][h], bl[b][h]);
-        }
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          mma_tf32_m16n8k8(acc[mt][nt], al[2 * mt][0], al[2 * mt + 1][0], al[2 * mt][1], al[2 * mt + 1][1], bh[nt][0], bh[nt][1]);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          mma_tf32_m16n8k8(acc[mt][nt], ah[2 * mt][0], ah[2 * mt + 1][0], ah[2 * mt][1], ah[2 * mt + 1][1], bl[nt][0], bl[nt][1]);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          mma_tf32_m16n8k8(acc[mt][nt], ah[2 * mt][0], ah[2 * mt + 1][0], ah[2 * mt][1], ah[2 * mt + 1][1], bh[nt][0], bh[nt][1]);
-      col0 += 8 * (long)lda;
-      col1 += 8 * (long)lda;
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float *q = acc_w + (16 * mt + fr) * LD + 8 * nt + 2 * fk;
-      q[0] = acc[mt][nt][0];
-      q[1] = acc[mt][nt][1];
-      q[8 * LD] = acc[mt][nt][2];
-      q[8 * LD + 1] = acc[mt][nt][3];
-    }
-}
-
 // resident warps per SM the register allocation is sized for: fp64 keeps 16 x 2 accumulators + a
 // prefetch window live and needs the full 255 registers (8 warps); measured n = 64 / 128 / 256:
 // 16 warps (128 regs, spills) 4.8 / 8.5 / 10.8 TFLOP/s, 12 warps 5.4 / 9.6 / 12.4, 8 warps 5.5 / 9.5 / 14.6
@@ -336,22 +186,16 @@ struct PanelMmaOcc {
   static constexpr int warps_per_sm = sizeof(T) == 8 ? KX_PANEL_WARPS_PER_SM : KX_PANEL_WARPS_PER_SM_F32;
 };
 
-template <typename T, int THREADS, bool STRIDED, bool TMA = false>
-__global__ void __launch_bounds__(THREADS, TMA ? (sizeof(T) == 8 ? 6 : 8) : (32 * PanelMmaOcc<T>::warps_per_sm) / THREADS)
+template <typename T, int THREADS, bool STRIDED>
+__global__ void __launch_bounds__(THREADS, (32 * PanelMmaOcc<T>::warps_per_sm) / THREADS)
 potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
                        const int info_mode) {
-  static_assert(!TMA || THREADS == 32, "the TMA-staged variant is the one-warp-per-matrix kernel");
   constexpr int NB = 32;
-  constexpr int LD = PanelMmaSmem<T, THREADS, TMA>::LD;
+  constexpr int LD = PanelMmaSmem<T, THREADS>::LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *Lkk = reinterpret_cast<T *>(smem_raw);  // factored diagonal block, column-major, identity padded
   T *invd = Lkk + NB * NB;                    // 1 / diag(L_JJ)
   T *accs = invd + NB;                        // per warp: 32 x LD transpose buffer
-  // TMA variant: double-buffered operand chunk + two mbarriers behind the per-warp buffers
-  T *Bs = reinterpret_cast<T *>(smem_raw + ((PanelMmaSmem<T, THREADS, TMA>::base + 15) / 16) * 16);
-  const uint32_t bs_addr = (uint32_t)__cvta_generic_to_shared(Bs);
-  const uint32_t bar_addr = bs_addr + (uint32_t)PanelMmaSmem<T, THREADS, TMA>::stage;
-  uint32_t ph0 = 0, ph1 = 0;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -359,16 +203,6 @@ potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, co
   T *__restrict__ A = Aref.at(blockIdx.x);
   T *acc_w = accs + warp * NB * LD;
   int bad = 0;
-  bool tma_ok = false;
-  if constexpr (TMA) {
-    tma_ok = (n % NB == 0) && ((reinterpret_cast<unsigned long long>(A) | ((unsigned long long)lda * sizeof(T))) & 15ull) == 0;
-    if (threadIdx.x == 0) {
-      mbar_init(bar_addr);
-      mbar_init(bar_addr + 8);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-  }
 
   for (int j0 = 0; j0 < n; j0 += NB) {
     const int jb = (n - j0 < NB) ? (n - j0) : NB;
@@ -399,8 +233,7 @@ potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, co
       }
 #endif
       if (warp_has_rows && j0 > 0) {
-        if (TMA && tma_ok) panel_update_mma_tma(acc_w, LD, A, lda, wrow0, j0, lane, Bs, bs_addr, bar_addr, ph0, ph1);
-        else panel_update_mma(acc_w, LD, A, lda, n, wrow0, j0, lane);
+        panel_update_mma(acc_w, LD, A, lda, n, wrow0, j0, lane);
       }
       __syncwarp();
 
@@ -449,7 +282,6 @@ potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, co
     }
     // the factored panel must be visible to the whole CTA before panel J+1 reads it from global
     __threadfence_block();
-    if constexpr (TMA) asm volatile("fence.proxy.async;" ::: "memory");  // ... and to the bulk copies (async proxy)
     __syncthreads();
   }
   if (info_mode && tid == 0) info[blockIdx.x] = bad;

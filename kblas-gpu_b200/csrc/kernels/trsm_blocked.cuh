@@ -163,7 +163,6 @@ template <typename T, bool LEFT, int OP, int GP, int WARPS, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32)
 tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                          BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
-  constexpr int NB = 32;
   constexpr int MPW = 32 / GP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;

@@ -26,7 +26,6 @@
 
 namespace kblasx {
 
-enum TriOp { TRI_FORWARD = 0, TRI_BACKWARD = 1, TRI_BOTH = 2 };
 
 // ptxas hoists the (volatile) shared-memory loads of later columns far ahead of the FMAs that
 // consume them; unbounded, that costs > 200 registers or even kilobytes of spills for the fused

@@ -42,11 +42,11 @@ static int posv_batch_strided(KBlasHandle *h, char side, char uplo, int m, int n
 }
 
 template <typename T>
-static int posv_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, T **A, int lda, T **B, int ldb,
-                           int batchCount, int *info) {
+static int posv_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, T **A, long a_off, int lda, T **B,
+                           long b_off, int ldb, int batchCount, int *info) {
   if (posv_ws_check(h, false, side, m, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
-  BatchRef<T, false> a = {A, 0};
-  BatchRef<T, false> b = {B, 0};
+  BatchRef<T, false> a = {A, a_off};
+  BatchRef<T, false> b = {B, b_off};
   return posv_batch_core<T, false>(h, side, uplo, m, n, a, lda, b, ldb, batchCount, info);
 }
 
@@ -56,7 +56,7 @@ static int posv_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, T
 #define KX_POSV_API(P, T)                                                                                      \
   int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n, T **A, int lda,   \
                        T **B, int ldb, int batchCount, int *info_array) {                                      \
-    return kblasx::posv_batch_ptrs<T>(handle, side, uplo, m, n, A, lda, B, ldb, batchCount, info_array);       \
+    return kblasx::posv_batch_ptrs<T>(handle, side, uplo, m, n, A, 0, lda, B, 0, ldb, batchCount, info_array);       \
   }                                                                                                            \
   int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n, T *A, int lda,    \
                        long strideA, T *B, int ldb, long strideB, int batchCount, int *info_array) {           \
@@ -65,7 +65,7 @@ static int posv_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, T
   }                                                                                                            \
   extern "C" int kblas##P##posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,    \
                                       T **A, int lda, T **B, int ldb, int batchCount, int *info_array) {       \
-    return kblasx::posv_batch_ptrs<T>(handle, side, uplo, m, n, A, lda, B, ldb, batchCount, info_array);       \
+    return kblasx::posv_batch_ptrs<T>(handle, side, uplo, m, n, A, 0, lda, B, 0, ldb, batchCount, info_array);       \
   }                                                                                                            \
   extern "C" int kblas##P##posv_batch_strided(kblasHandle_t handle, char side, char uplo, const int m,         \
                                               const int n, T *A, int lda, long strideA, T *B, int ldb,         \
@@ -73,5 +73,23 @@ static int posv_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, T
     return kblasx::posv_batch_strided<T>(handle, side, uplo, m, n, A, lda, strideA, B, ldb, strideB,           \
                                          batchCount, info_array);                                              \
   }
+// internal C++ entry points with sub-matrix offsets (reference Xposv_batch.cu:42-67, 112-138)
+#define KX_POSV_OFFSET_API(T)                                                                                   \
+  int Xposv_batch_offset(kblasHandle_t handle, char side, char uplo, const int m, const int n, T **A,           \
+                         int A_row_off, int A_col_off, int lda, T **B, int B_row_off, int B_col_off, int ldb,   \
+                         int batchCount, int *info_array) {                                                     \
+    return kblasx::posv_batch_ptrs<T>(handle, side, uplo, m, n, A, A_row_off + (long)A_col_off * lda, lda, B,   \
+                                      B_row_off + (long)B_col_off * ldb, ldb, batchCount, info_array);          \
+  }                                                                                                             \
+  int Xposv_batch_offset(kblasHandle_t handle, char side, char uplo, const int m, const int n, T *A,            \
+                         int A_row_off, int A_col_off, int lda, long strideA, T *B, int B_row_off,              \
+                         int B_col_off, int ldb, long strideB, int batchCount, int *info_array) {               \
+    return kblasx::posv_batch_strided<T>(handle, side, uplo, m, n, A + A_row_off + (long)A_col_off * lda, lda,  \
+                                         strideA, B + B_row_off + (long)B_col_off * ldb, ldb, strideB,          \
+                                         batchCount, info_array);                                               \
+  }
+KX_POSV_OFFSET_API(float)
+KX_POSV_OFFSET_API(double)
+
 KX_POSV_API(S, float)
 KX_POSV_API(D, double)

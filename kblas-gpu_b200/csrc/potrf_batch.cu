@@ -7,7 +7,6 @@
 #include "kblas.h"
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
-#include "kernels/potrf_panel.cuh"
 #include "kernels/potrf_panel_mma.cuh"
 #include "potrf_batch.h"
 
@@ -21,20 +20,9 @@ static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T,
   auto kern = potrf_reg_kernel<T, NP, G, WARPS, MINB, STRIDED, EXACT, LOCKSTEP>;
   // persistent CTAs: one resident wave, each CTA strides over its share of the batch
   const long need = (batchCount + per_cta - 1) / per_cta;
-  static int ctas_per_sm = 0;  // per instantiation
-  if (ctas_per_sm == 0) {
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, 0);
-    ctas_per_sm = occ > 0 ? occ : MINB;
-  }
-  const long wave = (long)h->sm_count * ctas_per_sm;
+  const long wave = (long)h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, 0, MINB);
   const long grid = need < wave ? need : wave;
-  static int stagger = -1;  // ns; env KBLAS_B200_STAGGER_NS (tuning)
-  if (stagger < 0) {
-    const char *e = getenv("KBLAS_B200_STAGGER_NS");
-    stagger = e ? atoi(e) : 0;
-  }
-  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode, (unsigned)stagger);
+  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(n, A, lda, batchCount, info, h->info_mode, 0u);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -49,107 +37,52 @@ static int launch_potrf_reg(KBlasHandle *h, const char *name, int n, BatchRef<T,
 
 // n <= 32: register-resident kernel, padded size NP = roundup(n, 8).  The EXACT instantiation
 // (n == NP, info untouched) carries no bounds predicates; everything else takes the generic one.
+// KBLAS_B200_ELEMENT_EXACT_STORES=1 (handle->exact_stores) also selects the generic one: it never writes a
+// strict-upper element, for callers that update the upper triangle concurrently.
 template <typename T, bool STRIDED>
 static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
-  const int v = h->variant_override;
-  const bool exact = (n % 8 == 0) && (h->info_mode == KBLASX_INFO_COMPAT);
+  const bool exact = (n % 8 == 0) && (h->info_mode == KBLASX_INFO_COMPAT) && !h->exact_stores;
   constexpr bool F32 = sizeof(T) == 4;
   if (n <= 8) return exact ? KX_LAUNCH_REG(8, 8, 4, 4, true, false) : KX_LAUNCH_REG(8, 8, 4, 4, false, false);
-  if (n <= 16) {
-    if (!exact) return KX_LAUNCH_REG(16, 8, 4, 4, false, true);
-    switch (v) {
-      case 1: return KX_LAUNCH_REG(16, 8, 8, 2, true, true);
-      default: return KX_LAUNCH_REG(16, 8, 4, 4, true, true);
-    }
-  }
+  if (n <= 16) return exact ? KX_LAUNCH_REG(16, 8, 4, 4, true, true) : KX_LAUNCH_REG(16, 8, 4, 4, false, true);
   if (n <= 24) {
     if (!exact) return KX_LAUNCH_REG(24, 8, 4, 3, false, true);
     // measured (B200, batch 2^20): fp64 one 8-warp lockstep CTA per SM 0.59 vs 3 x 4 warps 0.52;
     // fp32 the other way round (0.45 vs 0.49)
-    switch (v) {
-      case 1: return F32 ? KX_LAUNCH_REG(24, 8, 8, 1, true, true) : KX_LAUNCH_REG(24, 8, 4, 3, true, true);
-      case 2: return KX_LAUNCH_REG(24, 8, 8, 2, true, true);
-      default: return F32 ? KX_LAUNCH_REG(24, 8, 4, 3, true, true) : KX_LAUNCH_REG(24, 8, 8, 1, true, true);
-    }
+    return F32 ? KX_LAUNCH_REG(24, 8, 4, 3, true, true) : KX_LAUNCH_REG(24, 8, 8, 1, true, true);
   }
   if constexpr (F32) {
     // fp32: 80 values per lane fit a 128-register budget -> 16 resident warps per SM
-    if (!exact) return KX_LAUNCH_REG(32, 8, 4, 4, false, true);
-    switch (v) {
-      case 1: return KX_LAUNCH_REG(32, 8, 4, 4, true, true);
-      case 3: return KX_LAUNCH_REG(32, 16, 4, 4, true, true);
-      default: return KX_LAUNCH_REG(32, 8, 8, 2, true, true);
-    }
+    return exact ? KX_LAUNCH_REG(32, 8, 8, 2, true, true) : KX_LAUNCH_REG(32, 8, 4, 4, false, true);
   } else {
     // fp64: 160 registers of matrix data per lane -> one 8-warp CTA per SM, warps in lockstep
-    if (!exact) return KX_LAUNCH_REG(32, 8, 4, 2, false, true);
-    switch (v) {
-      case 1: return KX_LAUNCH_REG(32, 8, 4, 2, true, true);
-      case 3: return KX_LAUNCH_REG(32, 16, 4, 3, true, true);
-      default: return KX_LAUNCH_REG(32, 8, 8, 1, true, true);
-    }
+    return exact ? KX_LAUNCH_REG(32, 8, 8, 1, true, true) : KX_LAUNCH_REG(32, 8, 4, 2, false, true);
   }
 }
 
-// n > 32: one CTA per matrix, left-looking 32-column panels (kernels/potrf_panel.cuh)
-template <typename T, int THREADS, int R, bool STRIDED>
-static int launch_potrf_panel(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
-                              int *info) {
-  potrf_panel_kernel<T, THREADS, R, STRIDED><<<(unsigned)batchCount, THREADS, 0, h->stream>>>(n, A, lda, batchCount, info,
-                                                                                            h->info_mode);
-  h->note_launch(name);
-  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
-  return KBLAS_Success;
-}
-
-// n > 32, default: same panel algorithm with the update on the mma.sync tensor path -- DMMA for fp64,
-// 3 x TF32 for fp32 (kernels/potrf_panel_mma.cuh)
-template <typename T, int THREADS, bool STRIDED, bool TMA = false>
+// n > 32: left-looking 32-column panels, one warp per matrix, update on the mma.sync tensor path -- DMMA for
+// fp64, 3 x TF32 for fp32 (kernels/potrf_panel_mma.cuh)
+template <typename T, int THREADS, bool STRIDED>
 static int launch_potrf_panel_mma(KBlasHandle *h, const char *name, int n, BatchRef<T, STRIDED> A, int lda, int batchCount,
                                   int *info) {
-  auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED, TMA>;
-  const size_t smem = PanelMmaSmem<T, THREADS, TMA>::bytes;
-  // per instantiation AND per device: the attribute belongs to the device's context (one process may drive
-  // several GPUs, one handle each, as the reference harness does)
-  static bool attr_set[64] = {};
-  const int dev = (h->device_id >= 0 && h->device_id < 64) ? h->device_id : 0;
-  if (!attr_set[dev]) {
-    check_error_ret(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), KBLAS_CUDA_Error);
-    attr_set[dev] = true;
-  }
+  auto kern = potrf_panel_mma_kernel<T, THREADS, STRIDED>;
+  const size_t smem = PanelMmaSmem<T, THREADS>::bytes;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
   kern<<<(unsigned)batchCount, THREADS, smem, h->stream>>>(n, A, lda, batchCount, info, h->info_mode);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
 }
 
-#define KX_PANEL_MMA(TH)                                                                                              \
-  launch_potrf_panel_mma<T, TH, STRIDED>(h, sizeof(T) == 8 ? "potrf_panel_dmma<T=" #TH ">" : "potrf_panel_tf32x3<T=" #TH ">", \
-                                         n, A, lda, batchCount, info)
-
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
-  const int v = h->variant_override;
   // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
-  // pivot chain of the diagonal blocks (11..14 = tuning overrides)
+  // pivot chain of the diagonal blocks.
   // measured (B200, fp64, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,
   // 2 warps 2.9 / 6.1 / 9.7, 4 warps 1.5 / 4.5 / 8.9, 8 warps 0.8 / 2.5 / 6.6.  One warp with the
   // cap lifted to 255 registers (8 resident warps per SM, no spills): 5.5 / 9.5 / 14.6
-  if (v == 10)  // operand chunks staged by TMA bulk copies (experimental: needs n % 32 == 0, aligned columns; else falls back inside)
-    return launch_potrf_panel_mma<T, 32, STRIDED, true>(h, sizeof(T) == 8 ? "potrf_panel_dmma_tma<T=32>" : "potrf_panel_tf32x3_tma<T=32>",
-                                                        n, A, lda, batchCount, info);
-  if (v == 12) return KX_PANEL_MMA(64);
-  if (v == 13) return KX_PANEL_MMA(128);
-  if (v == 14) return KX_PANEL_MMA(256);
-  if (v != 9 && (v < 15 || v > 18)) return KX_PANEL_MMA(32);
-  // FMA-pipe panel kernel (A/B comparisons): 9 = one warp, 2 rows per thread
-  if constexpr (sizeof(T) == 4) {
-    if (v == 15) return launch_potrf_panel<T, 32, 4, STRIDED>(h, "potrf_panel<T=32,R=4>", n, A, lda, batchCount, info);
-    if (v == 16) return launch_potrf_panel<T, 64, 4, STRIDED>(h, "potrf_panel<T=64,R=4>", n, A, lda, batchCount, info);
-  }
-  if (v == 17) return launch_potrf_panel<T, 64, 2, STRIDED>(h, "potrf_panel<T=64,R=2>", n, A, lda, batchCount, info);
-  if (v == 18) return launch_potrf_panel<T, 128, 2, STRIDED>(h, "potrf_panel<T=128,R=2>", n, A, lda, batchCount, info);
-  return launch_potrf_panel<T, 32, 2, STRIDED>(h, "potrf_panel<T=32,R=2>", n, A, lda, batchCount, info);
+  return launch_potrf_panel_mma<T, 32, STRIDED>(h, sizeof(T) == 8 ? "potrf_panel_dmma<T=32>" : "potrf_panel_tf32x3<T=32>", n, A, lda,
+                                                batchCount, info);
 }
 
 // Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)
@@ -188,9 +121,9 @@ int potrf_batch_strided(KBlasHandle *h, char uplo, int n, T *A, int lda, long st
 }
 
 template <typename T>
-int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batchCount, int *info) {
+int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, long elem_off, int lda, int batchCount, int *info) {
   if (potrf_ws_check(h, false, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
-  BatchRef<T, false> ref = {A, 0};
+  BatchRef<T, false> ref = {A, elem_off};
   return potrf_batch_core<T, false>(h, uplo, n, ref, lda, batchCount, info);
 }
 
@@ -200,7 +133,7 @@ int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batch
 #define KX_POTRF_API(P, T)                                                                                    \
   int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount,         \
                         int *info_array) {                                                                    \
-    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, lda, batchCount, info_array);                      \
+    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, 0, lda, batchCount, info_array);                      \
   }                                                                                                           \
   int kblas_potrf_batch(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA,            \
                         int batchCount, int *info_array) {                                                    \
@@ -208,11 +141,27 @@ int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batch
   }                                                                                                           \
   extern "C" int kblas##P##potrf_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda,          \
                                        int batchCount, int *info_array) {                                     \
-    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, lda, batchCount, info_array);                      \
+    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, 0, lda, batchCount, info_array);                      \
   }                                                                                                           \
   extern "C" int kblas##P##potrf_batch_strided(kblasHandle_t handle, char uplo, const int n, T *A, int lda,   \
                                                long strideA, int batchCount, int *info_array) {               \
     return kblasx::potrf_batch_strided<T>(handle, uplo, n, A, lda, strideA, batchCount, info_array);          \
   }
+// internal C++ entry points with sub-matrix offsets that sibling routines and tests of the reference link against
+// (reference Xpotrf_batch.cu:44-63 pointer array, 107-127 strided; declared in src/Xblas_core.ch:249-262)
+#define KX_POTRF_OFFSET_API(T)                                                                                  \
+  int Xpotrf_batch_offset(kblasHandle_t handle, char uplo, const int n, T **A, int A_row_off, int A_col_off,    \
+                          int lda, int batchCount, int *info_array) {                                           \
+    return kblasx::potrf_batch_ptrs<T>(handle, uplo, n, A, A_row_off + (long)A_col_off * lda, lda, batchCount,  \
+                                       info_array);                                                             \
+  }                                                                                                             \
+  int Xpotrf_batch_offset(kblasHandle_t handle, char uplo, const int n, T *A, int A_row_off, int A_col_off,     \
+                          int lda, long strideA, int batchCount, int *info_array) {                             \
+    return kblasx::potrf_batch_strided<T>(handle, uplo, n, A + A_row_off + (long)A_col_off * lda, lda, strideA, \
+                                          batchCount, info_array);                                              \
+  }
+KX_POTRF_OFFSET_API(float)
+KX_POTRF_OFFSET_API(double)
+
 KX_POTRF_API(S, float)
 KX_POTRF_API(D, double)

@@ -9,5 +9,5 @@ int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, i
 template <typename T>
 int potrf_batch_strided(KBlasHandle *h, char uplo, int n, T *A, int lda, long strideA, int batchCount, int *info);
 template <typename T>
-int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, int lda, int batchCount, int *info);
+int potrf_batch_ptrs(KBlasHandle *h, char uplo, int n, T **A, long elem_off, int lda, int batchCount, int *info);
 }  // namespace kblasx

@@ -6,7 +6,6 @@
 // backward substitution run back to back on register-resident rows of B in one launch.
 #include "kblas.h"
 #include "kblas_common.h"
-#include "kernels/trsm_small.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -41,7 +40,7 @@ static int potrs_ws_check(KBlasHandle *h, bool strided, int m, int n, int batchC
 }
 
 template <typename T>
-static int potrs_batch_strided(KBlasHandle *h, char side, char uplo, int m, int n, const T *A, int lda, long strideA,
+int potrs_batch_strided(KBlasHandle *h, char side, char uplo, int m, int n, const T *A, int lda, long strideA,
                                T *B, int ldb, long strideB, int batchCount) {
   if (potrs_ws_check(h, true, m, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
   BatchRef<const T, true> a = {A, strideA};
@@ -50,11 +49,11 @@ static int potrs_batch_strided(KBlasHandle *h, char side, char uplo, int m, int 
 }
 
 template <typename T>
-static int potrs_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, const T **A, int lda, T **B, int ldb,
-                            int batchCount) {
+int potrs_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, const T **A, long a_off, int lda, T **B,
+                     long b_off, int ldb, int batchCount) {
   if (potrs_ws_check(h, false, m, n, batchCount) != KBLAS_Success) return KBLAS_InsufficientWorkspace;
-  BatchRef<const T, false> a = {A, 0};
-  BatchRef<T, false> b = {B, 0};
+  BatchRef<const T, false> a = {A, a_off};
+  BatchRef<T, false> b = {B, b_off};
   return potrs_batch_core<T, false>(h, side, uplo, m, n, a, lda, b, ldb, batchCount);
 }
 
@@ -64,7 +63,7 @@ static int potrs_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, 
 #define KX_POTRS_API(P, T)                                                                                     \
   int kblas_potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n, const T **A,     \
                         int lda, T **B, int ldb, int batchCount) {                                             \
-    return kblasx::potrs_batch_ptrs<T>(handle, side, uplo, m, n, A, lda, B, ldb, batchCount);                  \
+    return kblasx::potrs_batch_ptrs<T>(handle, side, uplo, m, n, A, 0, lda, B, 0, ldb, batchCount);                  \
   }                                                                                                            \
   int kblas_potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n, const T *A,      \
                         int lda, long strideA, T *B, int ldb, long strideB, int batchCount) {                  \
@@ -73,7 +72,7 @@ static int potrs_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, 
   }                                                                                                            \
   extern "C" int kblas##P##potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,   \
                                        const T **A, int lda, T **B, int ldb, int batchCount) {                 \
-    return kblasx::potrs_batch_ptrs<T>(handle, side, uplo, m, n, A, lda, B, ldb, batchCount);                  \
+    return kblasx::potrs_batch_ptrs<T>(handle, side, uplo, m, n, A, 0, lda, B, 0, ldb, batchCount);                  \
   }                                                                                                            \
   extern "C" int kblas##P##potrs_batch_strided(kblasHandle_t handle, char side, char uplo, const int m,        \
                                                const int n, const T *A, int lda, long strideA, T *B, int ldb,  \
@@ -81,5 +80,23 @@ static int potrs_batch_ptrs(KBlasHandle *h, char side, char uplo, int m, int n, 
     return kblasx::potrs_batch_strided<T>(handle, side, uplo, m, n, A, lda, strideA, B, ldb, strideB,          \
                                           batchCount);                                                         \
   }
+// internal C++ entry points with sub-matrix offsets (reference Xpotrs_batch.cu:42-58, 104-127; src/Xblas_core.ch:264-277)
+#define KX_POTRS_OFFSET_API(T)                                                                                  \
+  int Xpotrs_batch_offset(kblasHandle_t handle, char side, char uplo, const int m, const int n, const T **A,    \
+                          int A_row_off, int A_col_off, int lda, T **B, int B_row_off, int B_col_off, int ldb,  \
+                          int batchCount) {                                                                     \
+    return kblasx::potrs_batch_ptrs<T>(handle, side, uplo, m, n, A, A_row_off + (long)A_col_off * lda, lda, B,  \
+                                       B_row_off + (long)B_col_off * ldb, ldb, batchCount);                     \
+  }                                                                                                             \
+  int Xpotrs_batch_offset(kblasHandle_t handle, char side, char uplo, const int m, const int n, const T *A,     \
+                          int A_row_off, int A_col_off, int lda, long strideA, T *B, int B_row_off,             \
+                          int B_col_off, int ldb, long strideB, int batchCount) {                               \
+    return kblasx::potrs_batch_strided<T>(handle, side, uplo, m, n, A + A_row_off + (long)A_col_off * lda, lda, \
+                                          strideA, B + B_row_off + (long)B_col_off * ldb, ldb, strideB,         \
+                                          batchCount);                                                          \
+  }
+KX_POTRS_OFFSET_API(float)
+KX_POTRS_OFFSET_API(double)
+
 KX_POTRS_API(S, float)
 KX_POTRS_API(D, double)

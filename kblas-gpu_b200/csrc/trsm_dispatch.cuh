@@ -1,0 +1,155 @@
+// trsm_dispatch.cuh -- kernel selection of the triangular solves (trsm, potrs, posv), shared by the per-(precision,
+// layout, side) instantiation units trsm_inst_*.cu: the kernels are heavily unrolled templates, so the instantiations
+// are spread over eight translation units that compile in parallel.
+// Counterpart of the reference's kernel table + recursion, Xtrsm_batch_drivers.cuh:54-272.  Here: one launch per call.
+#pragma once
+#include "kblas.h"
+#include "kblas_common.h"
+#include "kernels/trsm_small.cuh"
+#include "kernels/trsm_blocked.cuh"
+#include "kernels/trsm_reg.cuh"
+#include "kernels/trsm_dual.cuh"
+#include "tri_batch.h"
+
+namespace kblasx {
+
+template <typename T, int NP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                            int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4;
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  const size_t smem = (size_t)WARPS * TriSmem<NP, LEFT>::per_warp * sizeof(T);
+  auto kern = tri_solve_small_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// full NP x NP factor: two vectors per lane, two problems per warp, cp.async staging (kernels/trsm_dual.cuh)
+template <typename T, int NP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                           BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = LEFT ? 2 : 4;  // side L carries a transpose tile per problem: 2-warp CTAs keep 3 CTAs per SM
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
+  const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
+  auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// k <= 16 and vec <= 16: register-resident, 2 / 4 problems per warp (kernels/trsm_reg.cuh)
+template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_reg(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                          int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;
+  const long wtasks = ((long)batchCount + MPW - 1) / MPW;
+  const long grid = (wtasks + WARPS - 1) / WARPS;
+  tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// vec <= 16: several matrices per warp (kernels/trsm_small.cuh, packed variant)
+template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_packed(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                             int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;
+  const long wtasks = ((long)batchCount + MPW - 1) / MPW;
+  const long grid = (wtasks + WARPS - 1) / WARPS;
+  tri_solve_packed_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>
+      <<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// k > 32: blocked substitution, one warp per (matrix, 32-vector slab), or 2 / 4 matrices per warp when
+// there are at most 16 / 8 right-hand-side vectors (kernels/trsm_blocked.cuh)
+template <typename T, bool LEFT, int OP, int GP, bool STRIDED>
+static int launch_tri_blocked_gp(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
+                                 int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  constexpr int MPW = 32 / GP;
+  constexpr size_t per_warp = TriBlockedSmem<T, GP>::per_warp * sizeof(T);
+  constexpr int WARPS = (per_warp * 4 <= 70000) ? 4 : (per_warp * 2 <= 70000) ? 2 : 1;
+  const int slabs = (GP == 32) ? (vec + 31) / 32 : 1;
+  const long tasks = (((long)batchCount + MPW - 1) / MPW) * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  auto kern = tri_solve_blocked_kernel<T, LEFT, OP, GP, WARPS, STRIDED>;
+  const size_t smem = per_warp * WARPS;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+template <typename T, bool LEFT, int OP, bool STRIDED>
+static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                              BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  if (vec <= 8)
+    return launch_tri_blocked_gp<T, LEFT, OP, 8, STRIDED>(h, "tri_blocked<GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (vec <= 16)
+    return launch_tri_blocked_gp<T, LEFT, OP, 16, STRIDED>(h, "tri_blocked<GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  return launch_tri_blocked_gp<T, LEFT, OP, 32, STRIDED>(h, "tri_blocked<GP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+}
+
+template <typename T, bool LEFT, int OP, bool STRIDED>
+static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                        BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  // measured (B200, 2^20 problems, side L): dual vs one-vector kernel  fp64 k=32 4.7-5.1 vs 5.1-5.4 ms, k=24 3.0-3.4 vs
+  // 3.6-3.9; fp32 k=24 2.07 vs 2.35 but k=32 2.96-3.07 vs 2.77-2.83 -> fp32 k=32 side L stays on the older kernel
+  const bool dual_ok = !LEFT || !(sizeof(T) == 4 && k == 32);
+  if (dual_ok) {
+    // k = 16 with <= 16 vectors leaves the second vector of every lane idle and still wins on side R (measured, ms per
+    // 2^20: fp64 potrs 1.07 vs 1.6-2.7, trsm R 0.95 vs 1.01-1.08; fp32 trsm R 0.57-0.59 vs 0.58-0.64); side L and fp32
+    // potrs stay on the register / packed kernels (dual: 1.4-1.5 vs 1.13-1.2; 0.76 vs 0.73)
+    const bool dual16 = vec > 16 || (!LEFT && (sizeof(T) == 8 || OP != TRI_BOTH));
+    if (k == 16 && dual16) return launch_tri_dual<T, 16, LEFT, OP, STRIDED>(h, "tri_dual<NP=16>", vec, alpha, A, lda, B, ldb, batchCount);
+    if (k == 24) return launch_tri_dual<T, 24, LEFT, OP, STRIDED>(h, "tri_dual<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
+    if (k == 32) return launch_tri_dual<T, 32, LEFT, OP, STRIDED>(h, "tri_dual<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
+  }
+  // few right-hand sides and a small factor: register kernel, 4 / 2 problems per warp
+  // (measured: the shared-memory packed kernel stays ahead only for fp32, side R, 8 < k <= 16)
+  if (!(sizeof(T) == 4 && !LEFT && k > 8)) {
+    if (k <= 8 && vec <= 8) return launch_tri_reg<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 8 && vec <= 16) return launch_tri_reg<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 16 && vec <= 16) return launch_tri_reg<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_reg<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
+  if (k <= 8 && vec <= 8) return launch_tri_packed<T, 8, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 8 && vec <= 16) return launch_tri_packed<T, 8, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=8,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  // (side L reads B by rows, one lane per row: the lane group must cover all k rows)
+  if constexpr (!LEFT) {
+    if (k <= 16 && vec <= 8) return launch_tri_packed<T, 16, 8, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
+  if (k <= 16 && vec <= 16) return launch_tri_packed<T, 16, 16, LEFT, OP, STRIDED>(h, "tri_packed<NP=16,GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  if (k <= 24) return launch_tri_small<T, 24, LEFT, OP, STRIDED>(h, "tri_small<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  return launch_tri_small<T, 32, LEFT, OP, STRIDED>(h, "tri_small<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+}
+
+// one side of tri_solve_core: LEFT fixed at compile time, op dispatched here
+template <typename T, bool STRIDED, bool LEFT>
+int tri_solve_side(KBlasHandle *h, int op, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
+                   BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+#define KX_TRI(O_)                                                                                   \
+  (k <= 32 ? tri_small_np<T, LEFT, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount)         \
+           : launch_tri_blocked<T, LEFT, O_, STRIDED>(h, k, vec, alpha, A, lda, B, ldb, batchCount))
+  if (op == TRI_FORWARD) return KX_TRI(TRI_FORWARD);
+  if (op == TRI_BACKWARD) return KX_TRI(TRI_BACKWARD);
+  return KX_TRI(TRI_BOTH);
+#undef KX_TRI
+}
+
+}  // namespace kblasx

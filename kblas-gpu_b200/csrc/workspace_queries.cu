@@ -77,6 +77,9 @@ void kblas_trsm_batch_wsquery(kblasHandle_t handle, char side, int m, int n, int
 void kblas_trsm_batch_strided_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount) {
   kblasx::trsm_batch_wsquery_core(true, batchCount, side, m, n, REQ(handle));
 }
+// non-uniform TRSM exists in the reference only through MAGMA (Xtrsm_batch_drivers.cuh:277-367); without
+// USE_MAGMA its query records nothing (src/workspace_queries.cu:268-277) -- same here
+void kblas_trsm_batch_nonuniform_wsquery(kblasHandle_t /*handle*/) {}
 void kblas_potrf_batch_wsquery(kblasHandle_t handle, const int n, int batchCount) {
   kblasx::potrf_batch_wsquery_core(false, n, batchCount, REQ(handle));
 }

@@ -265,49 +265,151 @@ def test_trsm_large_k(env, p, side, trans, k, other):
     assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
 
 
+def _slack_copy(torch, a, off):
+    """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
+    `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""
+    d = torch.zeros(a.size + off + 4, dtype=getattr(torch, a.dtype.name), device="cuda")
+    d[off:off + a.size] = torch.from_numpy(a).cuda().flatten()
+    return d
+
+
+def _ptrs(torch, d, off, perm, elems_per_matrix, itemsize):
+    return (d.data_ptr() + (off + perm * elems_per_matrix) * itemsize).contiguous()
+
+
 @pytest.mark.parametrize("p", ["D", "S"])
 @pytest.mark.parametrize("side,trans", [("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")])
-@pytest.mark.parametrize("k,vec", [(8, 8), (8, 5), (8, 16), (16, 16), (16, 3)])
-@pytest.mark.parametrize("layout", ["strided", "ptr_aligned", "ptr_offset1"])
-def test_trsm_small_packed_layout(env, p, side, trans, k, vec, layout, monkeypatch):
-    """lda == k (the north-star layout) on the L1-broadcast kernel (forced: by default it only serves fp64 potrs
-    k = 16); strided, pointer array, and a pointer array whose entries are NOT 16-byte aligned (one element past
-    an aligned address: the kernel's scalar path)."""
-    kb, _, torch = env
-    monkeypatch.setenv("KBLAS_B200_VARIANT", "7")
-    h = kb.Handle()
+@pytest.mark.parametrize("k", [5, 8, 13, 16, 24, 32, 40, 48])
+def test_trsm_pointer_array_default_kernels(env, p, side, trans, k):
+    """kblas?trsm_batch (pointer array) on the DEFAULT kernels -- no variant override -- with shuffled pointer arrays,
+    16-byte aligned and element-aligned-only (off by one element) matrices, lda == k and padded, few / many vectors.
+    Reference: Xtrsm_batch.cu:42-112."""
+    kb, h, torch = env
     dt = DT[p]
-    m, n = (k, vec) if side == "L" else (vec, k)
-    batch, alpha = 131, -1.7
-    A = U.rand_spd_batch(batch, k, dtype=dt, seed=k + 3)           # lda = k, stride k*k
-    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=m * 10 + n)      # ldb = m
-    Bo = B0.copy()
-    U.oracle_trsm(side, "L", trans, "N", m, n, alpha, A, Bo)
     es = np.dtype(dt).itemsize
-    off = 1 if layout == "ptr_offset1" else 0
-    # device copies with `off` elements of slack in front so that every matrix starts off-by-one
-    dA = torch.zeros(A.size + 4, dtype=getattr(torch, np.dtype(dt).name), device="cuda")
-    dB = torch.zeros(B0.size + 4, dtype=dA.dtype, device="cuda")
-    dA[off:off + A.size] = _dev(torch, A).flatten()
-    dB[off:off + B0.size] = _dev(torch, B0).flatten()
-    h.trsm_batch_wsquery(side, m, n, batch)
-    h.trsm_batch_strided_wsquery(side, m, n, batch)
-    h.allocate_workspace()
-    if layout == "strided":
-        rc = h.trsm_batch_strided(side, "L", trans, "N", m, n, alpha, dA, k, k * k, dB, m, m * n, batch)
-    else:
-        perm = torch.randperm(batch, device="cuda")
-        pa = (dA.data_ptr() + (off + perm * (k * k)) * es).contiguous()
-        pb = (dB.data_ptr() + (off + perm * (m * n)) * es).contiguous()
-        rc = h.trsm_batch(side, "L", trans, "N", m, n, alpha, pa, k, pb, m, batch, prec=p)
+    batch, alpha = 131, -1.7
+    seen = set()
+    for vec in (3, 16, 33):
+        for off, pad in ((0, 0), (1, 0), (1, 1)):
+            m, n = (k, vec) if side == "L" else (vec, k)
+            lda, ldb = k + pad, m + pad
+            A = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=k + 3)
+            B0 = U.rand_batch(batch, m, n, ld=ldb, dtype=dt, seed=m * 10 + n)
+            Bo = B0.copy()
+            U.oracle_trsm(side, "L", trans, "N", m, n, alpha, A, Bo)
+            dA, dB = _slack_copy(torch, A, off), _slack_copy(torch, B0, off)
+            perm = torch.randperm(batch, device="cuda")
+            pa, pb = _ptrs(torch, dA, off, perm, k * lda, es), _ptrs(torch, dB, off, perm, n * ldb, es)
+            h.trsm_batch_wsquery(side, m, n, batch)
+            h.allocate_workspace()
+            rc = h.trsm_batch(side, "L", trans, "N", m, n, alpha, pa, lda, pb, ldb, batch, prec=p)
+            torch.cuda.synchronize()
+            assert rc == kb.KBLAS_Success
+            seen.add(h.last_kernel.split("<")[0])
+            got = dB[off:off + B0.size].cpu().numpy().reshape(B0.shape)
+            tol = 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :m]).max())
+            assert np.abs(got[:, :, :m] - Bo[:, :, :m]).max() <= tol, (vec, off, pad, h.last_kernel)
+            assert np.array_equal(got[:, :, m:], B0[:, :, m:]), "ldb padding untouched"
+            assert np.array_equal(dA[off:off + A.size].cpu().numpy().reshape(A.shape), A), "A is read-only"
+            assert float(dB[:off].abs().sum()) == 0 and float(dB[off + B0.size:].abs().sum()) == 0, "slack untouched"
+    want = {"tri_blocked"} if k > 32 else ({"tri_dual"} if k in (16, 24, 32) and not (p == "S" and side == "L" and k == 32) else set())
+    assert want <= seen, (seen, want)
+    assert not any("bcast" in s for s in seen)
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [5, 8, 16, 24, 32, 48])
+def test_potrs_posv_pointer_array_default_kernels(env, p, n):
+    """kblas?potrs_batch and kblas?posv_batch, pointer-array form, n <= 32 and the first blocked size, shuffled and
+    off-by-one-element pointers.  Reference: Xpotrs_batch.cu:42-101, Xposv_batch.cu:42-107."""
+    kb, h, torch = env
+    dt = DT[p]
+    es = np.dtype(dt).itemsize
+    batch = 97
+    for m in (3, 16, 40):
+        for off in (0, 1):
+            A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n + 1)
+            B0 = U.rand_batch(batch, m, n, dtype=dt, seed=n + 2 + m)
+            Ao, Bo = A0.copy(), B0.copy()
+            U.oracle_posv("R", "L", m, n, Ao, Bo)
+            tol = 100 * n * U.EPS[dt] * max(1.0, np.abs(Bo).max())
+            perm = torch.randperm(batch, device="cuda")
+            # potrs from the oracle's factor
+            dL, dB = _slack_copy(torch, Ao, off), _slack_copy(torch, B0, off)
+            pa, pb = _ptrs(torch, dL, off, perm, n * n, es), _ptrs(torch, dB, off, perm, m * n, es)
+            h.posv_batch_wsquery("R", m, n, batch)
+            h.potrs_batch_wsquery(m, n, batch)
+            h.allocate_workspace()
+            assert h.potrs_batch("R", "L", m, n, pa, n, pb, m, batch, prec=p) == kb.KBLAS_Success
+            torch.cuda.synchronize()
+            got = dB[off:off + B0.size].cpu().numpy().reshape(B0.shape)
+            assert np.abs(got - Bo).max() <= tol, ("potrs", m, off, h.last_kernel)
+            assert np.array_equal(dL[off:off + Ao.size].cpu().numpy().reshape(Ao.shape), Ao), "factor is read-only"
+            # posv from A
+            dA, dB2 = _slack_copy(torch, A0, off), _slack_copy(torch, B0, off)
+            pa, pb = _ptrs(torch, dA, off, perm, n * n, es), _ptrs(torch, dB2, off, perm, m * n, es)
+            info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+            assert h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, info, prec=p) == kb.KBLAS_Success
+            torch.cuda.synchronize()
+            _check_potrf(A0, dA[off:off + A0.size].cpu().numpy().reshape(A0.shape), n, dt, Lref=Ao)
+            got = dB2[off:off + B0.size].cpu().numpy().reshape(B0.shape)
+            assert np.abs(got - Bo).max() <= tol, ("posv", m, off, h.last_kernel)
+            assert (info.cpu().numpy() == SENT).all()
+
+
+def test_pointer_and_value_helpers(env):
+    """Xset_pointer_{1,2,3} / iset_value_{1,2,4,5} (reference Xhelper_funcs.cu:74-105, kblas_common.cu:344-386)"""
+    kb, h, torch = env
+    batch = 1000
+    bases = [torch.zeros(16, dtype=torch.float64, device="cuda") for _ in range(3)]
+    outs = [torch.zeros(batch, dtype=torch.int64, device="cuda") for _ in range(3)]
+    offs = [64, 7, 1024]
+    i = torch.arange(batch, dtype=torch.int64, device="cuda")
+    assert h.set_pointer_1(outs[0], bases[0], 8, offs[0], batch) == kb.KBLAS_Success
     torch.cuda.synchronize()
-    assert rc == kb.KBLAS_Success
-    assert ("tri_bcast" in h.last_kernel) == (k in (8, 16)), h.last_kernel
-    got = dB[off:off + B0.size].cpu().numpy().reshape(B0.shape)
-    assert np.abs(got - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
-    assert np.array_equal(dA[off:off + A.size].cpu().numpy().reshape(A.shape), A), "A is read-only"
-    assert float(dB[:off].abs().sum()) == 0 and float(dB[off + B0.size:].abs().sum()) == 0, "slack untouched"
-    h.destroy()
+    assert torch.equal(outs[0], bases[0].data_ptr() + i * offs[0] * 8)
+    for o in outs:
+        o.zero_()
+    assert h.set_pointer_2(outs[0], bases[0], 8, offs[0], outs[1], bases[1], 8, offs[1], batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    for q in range(2):
+        assert torch.equal(outs[q], bases[q].data_ptr() + i * offs[q] * 8)
+    for o in outs:
+        o.zero_()
+    assert h.set_pointer_3(outs[0], bases[0], 8, offs[0], outs[1], bases[1], 8, offs[1], outs[2], bases[2], 8, offs[2], batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    for q in range(3):
+        assert torch.equal(outs[q], bases[q].data_ptr() + i * offs[q] * 8)
+    # fp32 flavour: element size 4
+    f32 = torch.zeros(16, dtype=torch.float32, device="cuda")
+    assert h.set_pointer_1(outs[0], f32, 8, 5, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], f32.data_ptr() + i * 5 * 4)
+    for count in (1, 2, 4, 5):
+        arrs = [torch.zeros(batch, dtype=torch.int32, device="cuda") for _ in range(count)]
+        assert h.iset_values([(a, 11 + q) for q, a in enumerate(arrs)], batch) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        for q, a in enumerate(arrs):
+            assert bool((a == 11 + q).all())
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+def test_trsm_alpha_zero_is_blas_semantics(env, p):
+    """alpha == 0: B := 0 for every variant and size (BLAS semantics).  Documented deviation (SURVEY Appendix A,
+    DESIGN.md §1): the reference's recursion multiplies by -1/alpha for side R / trans T and k > 16
+    (Xtrsm_batch_drivers.cuh:154-163) and returns Inf/NaN there; for k <= 16 it also returns zeros."""
+    kb, h, torch = env
+    dt = DT[p]
+    for side, trans in (("L", "N"), ("L", "T"), ("R", "N"), ("R", "T")):
+        for k in (8, 16, 32, 64):
+            m, n, batch = k, k, 33
+            A = U.rand_spd_batch(batch, k, dtype=dt, seed=k)
+            dA, dB = _dev(torch, A), _dev(torch, U.rand_batch(batch, m, n, dtype=dt, seed=3))
+            h.trsm_batch_strided_wsquery(side, m, n, batch)
+            h.allocate_workspace()
+            assert h.trsm_batch_strided(side, "L", trans, "N", m, n, 0.0, dA, k, k * k, dB, m, m * n, batch) == kb.KBLAS_Success
+            torch.cuda.synchronize()
+            assert bool((dB == 0).all()), (side, trans, k)
 
 
 def test_trsm_potrs_random_shapes(env):
@@ -547,6 +649,65 @@ def test_live_against_reference_library(env, p):
     ref.close()
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_live_large_n_against_reference_library(env, p, n):
+    """BASELINE config 4 sizes, live against the unmodified reference library on identical device buffers: potrf
+    (strided + pointer array) and posv with m = 16 right-hand-side rows (pointer array, shuffled).  The reference goes
+    through cuBLAS batched GEMM here, so equality is tolerance-based: |L - L_ref| <= 100 n eps ||A||."""
+    if not U.have_ref():
+        pytest.skip("oracle/_ref/libkblas_ref.so not built (needs /root/reference at build time)")
+    kb, h, torch = env
+    dt = DT[p]
+    es = np.dtype(dt).itemsize
+    ref = U.RefLib()
+    H, i, l, c, P = ref.H, ref.i, ref.l, ref.c, ref.P
+    r_potrf = ref.fn(f"kblas{p}potrf_batch_strided", [H, c, i, P, i, l, i, P])
+    r_potrf_p = ref.fn(f"kblas{p}potrf_batch", [H, c, i, P, i, i, P])
+    r_posv_p = ref.fn(f"kblas{p}posv_batch", [H, c, c, i, i, P, i, P, i, i, P])
+    m, batch = 16, 61
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n)
+    B0 = U.rand_batch(batch, m, n, dtype=dt, seed=n + 1)
+    ref.wsquery("kblas_posv_batch_wsquery", "ciii", b"R", m, n, batch)
+    ref.wsquery("kblas_posv_batch_strided_wsquery", "ciii", b"R", m, n, batch)
+    ref.allocate()
+    h.posv_batch_wsquery("R", m, n, batch)
+    h.posv_batch_strided_wsquery("R", m, n, batch)
+    h.allocate_workspace()
+    perm = np.random.default_rng(n).permutation(batch).astype(np.int64)
+    # strided potrf
+    mine_A, ref_A = _dev(torch, A0), _dev(torch, A0)
+    assert r_potrf(ref.h, b"L", n, ref_A.data_ptr(), n, n * n, batch, None) == 1
+    assert h.potrf_batch_strided("L", n, mine_A, n, n * n, batch, None) == 1
+    torch.cuda.synchronize()
+    _check_potrf(A0, mine_A.cpu().numpy(), n, dt, Lref=ref_A.cpu().numpy())
+    # pointer-array potrf
+    mine_A, ref_A = _dev(torch, A0), _dev(torch, A0)
+    pm = torch.from_numpy(mine_A.data_ptr() + perm * n * n * es).cuda()
+    pr = torch.from_numpy(ref_A.data_ptr() + perm * n * n * es).cuda()
+    assert r_potrf_p(ref.h, b"L", n, pr.data_ptr(), n, batch, None) == 1
+    assert h.potrf_batch("L", n, pm, n, batch, None, prec=p) == 1
+    torch.cuda.synchronize()
+    _check_potrf(A0, mine_A.cpu().numpy(), n, dt, Lref=ref_A.cpu().numpy())
+    # pointer-array posv
+    mine_A, ref_A = _dev(torch, A0), _dev(torch, A0)
+    mine_B, ref_B = _dev(torch, B0), _dev(torch, B0)
+    pm = torch.from_numpy(mine_A.data_ptr() + perm * n * n * es).cuda()
+    pr = torch.from_numpy(ref_A.data_ptr() + perm * n * n * es).cuda()
+    pmb = torch.from_numpy(mine_B.data_ptr() + perm * m * n * es).cuda()
+    prb = torch.from_numpy(ref_B.data_ptr() + perm * m * n * es).cuda()
+    info_m = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    info_r = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    assert r_posv_p(ref.h, b"R", b"L", m, n, pr.data_ptr(), n, prb.data_ptr(), m, batch, info_r.data_ptr()) == 1
+    assert h.posv_batch("R", "L", m, n, pm, n, pmb, m, batch, info_m, prec=p) == 1
+    torch.cuda.synchronize()
+    _check_potrf(A0, mine_A.cpu().numpy(), n, dt, Lref=ref_A.cpu().numpy())
+    t = ref_B.cpu().numpy()
+    assert np.abs(mine_B.cpu().numpy() - t).max() <= 100 * n * U.EPS[dt] * max(1.0, np.abs(t).max())
+    assert torch.equal(info_m, info_r)
+    ref.close()
+
+
 # =============================================================================================
 # BASELINE.json full sizes through size-independent properties
 @pytest.mark.parametrize("p,n,batch", [("D", 32, 1 << 20), ("D", 8, 1 << 20), ("D", 16, 1 << 20), ("D", 24, 1 << 20), ("S", 32, 1 << 20)])
@@ -580,6 +741,79 @@ def test_full_size_potrf_potrs_properties(env, p, n, batch):
         assert res <= 10 * n * eps, (lo, res)
         Xm, Bm = B[sl].transpose(1, 2).double(), B0[sl].transpose(1, 2).double()
         R2 = Xm @ Am - Bm                                          # X A = B
+        res2 = (R2.flatten(1).norm(dim=1) / (Am.flatten(1).norm(dim=1) * Xm.flatten(1).norm(dim=1))).max().item()
+        assert res2 <= 10 * n * eps, (lo, res2)
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+def test_full_size_config3_trsm_left(env, p):
+    """config 3: strided trsm side L, uplo L, n = 32, nrhs = 32, batch = 1M, fp32 and fp64; residual
+    ||L X - alpha B|| / (||L|| ||X||) on slices, finiteness over the whole batch."""
+    kb, h, torch = env
+    n, batch, alpha = 32, 1 << 20, 0.28
+    tdt = torch.float64 if p == "D" else torch.float32
+    eps = U.EPS[DT[p]]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdt)
+    A.diagonal(dim1=1, dim2=2).add_(n)            # memory [b, col, row]: lower factor = torch.triu of A[b]
+    B = torch.rand((batch, n, n), generator=g, device="cuda", dtype=tdt)
+    B0 = B.clone()
+    h.trsm_batch_strided_wsquery("L", n, n, batch)
+    h.allocate_workspace()
+    for trans in ("N", "T"):
+        B.copy_(B0)
+        assert h.trsm_batch_strided("L", "L", trans, "N", n, n, alpha, A, n, n * n, B, n, n * n, batch) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(B).all())
+        for lo in (0, batch // 2 - 2048, batch - 4096):
+            sl = slice(lo, lo + 4096)
+            Lm = torch.triu(A[sl]).transpose(1, 2).double()
+            if trans == "T":
+                Lm = Lm.transpose(1, 2)
+            Xm, Bm = B[sl].transpose(1, 2).double(), B0[sl].transpose(1, 2).double()
+            R = Lm @ Xm - alpha * Bm
+            res = (R.flatten(1).norm(dim=1) / (Lm.flatten(1).norm(dim=1) * Xm.flatten(1).norm(dim=1))).max().item()
+            assert res <= 10 * n * eps, (trans, lo, res)
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_full_size_config4_posv_pointer_array(env, n):
+    """config 4: pointer-array dposv, n = 64 / 128 / 256, 16 right-hand-side rows, batch = 64K (shuffled pointers);
+    factor residual and solve residual X A = B on slices, finiteness + untouched strict upper over all of it."""
+    kb, h, torch = env
+    m, batch = 16, 1 << 16
+    eps = U.EPS[np.float64]
+    g = torch.Generator(device="cuda").manual_seed(n)
+    A = torch.empty((batch, n, n), device="cuda", dtype=torch.float64)
+    for lo in range(0, batch, 1 << 13):
+        a = torch.rand((1 << 13, n, n), generator=g, device="cuda", dtype=torch.float64)
+        a = torch.tril(a) + torch.tril(a, -1).transpose(1, 2)
+        a.diagonal(dim1=1, dim2=2).add_(n)
+        A[lo:lo + (1 << 13)] = a
+    A0 = A.clone()
+    B = torch.rand((batch, n, m), generator=g, device="cuda", dtype=torch.float64)
+    B0 = B.clone()
+    perm = torch.randperm(batch, device="cuda")
+    pa = (A.data_ptr() + perm * (n * n * 8)).contiguous()
+    pb = (B.data_ptr() + perm * (m * n * 8)).contiguous()
+    h.posv_batch_wsquery("R", m, n, batch)
+    h.allocate_workspace()
+    assert h.posv_batch("R", "L", m, n, pa, n, pb, m, batch, None, prec="D") == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(B).all())
+    for lo in range(0, batch, 1 << 12):      # chunked: the n = 256 batch is 32 GiB, twice with the pristine copy
+        sl = slice(lo, lo + (1 << 12))
+        assert bool(torch.isfinite(A[sl]).all())
+        assert torch.equal(torch.tril(A[sl], -1), torch.tril(A0[sl], -1)), "strict upper triangle modified"
+    for lo in (0, batch // 2 - 256, batch - 512):
+        sl = slice(lo, lo + 512)
+        Lm = torch.triu(A[sl]).transpose(1, 2)
+        Am = A0[sl].transpose(1, 2)
+        R = Am - Lm @ Lm.transpose(1, 2)
+        res = (R.flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item()
+        assert res <= 10 * n * eps, (lo, res)
+        Xm, Bm = B[sl].transpose(1, 2), B0[sl].transpose(1, 2)
+        R2 = Xm @ Am - Bm
         res2 = (R2.flatten(1).norm(dim=1) / (Am.flatten(1).norm(dim=1) * Xm.flatten(1).norm(dim=1))).max().item()
         assert res2 <= 10 * n * eps, (lo, res2)
 

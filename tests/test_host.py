@@ -60,9 +60,12 @@ def test_mangled_cpp_symbols_match_the_reference_abi(built):
     if U.have_ref():
         out = subprocess.check_output(["nm", "-D", "--defined-only", U.REF_SO], text=True)
         theirs = {l.split()[-1] for l in out.splitlines() if l.strip()}
-        hot = [s for s in theirs if re.search(r"kblas_?(potrf|trsm|potrs|posv)_batch|kblas[SD](potrf|trsm|potrs|posv)_batch", s)
-               and "core" not in s and "offset" not in s and "Xtrsm" not in s and "nonuniform" not in s
-               and not re.search(r"(PPi|Pii|PiS)", s)      # non-uniform overloads (MAGMA-only path, out of scope)
+        # every s/d symbol of the hot path the reference library exports: public calls, wsqueries, the internal offset
+        # entry points, the pointer / value helpers -- non-uniform (MAGMA-only) trsm overloads included
+        hot = [s for s in theirs
+               if re.search(r"kblas_?(potrf|trsm|potrs|posv)_batch|kblas[SD](potrf|trsm|potrs|posv)_batch|"
+                            r"X(potrf|potrs|posv)_batch_offset|Xtrsm_batch|iset_value_[1245]|Xset_pointer_[123]P", s)
+               and "core" not in s
                and "cuComplex" not in s and "6float2" not in s and "7double2" not in s]
         absent = sorted(s for s in hot if s not in ours)
         assert not absent, absent

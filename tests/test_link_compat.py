@@ -1,0 +1,95 @@
+"""Link-level drop-in checks.
+
+* a C++ translation unit (tests/cpp/link_compat.cpp) compiled against include/kblas.h + include/kblas_internal.h and
+  linked with libkblas-gpu.so -- CPU: compile, link, load; GPU: every offset entry point against the public call;
+* the reference's OWN test/bench programs (testing/batch_triangular/test_X{potrf,trsm,potrs,posv}_batch.cpp), built
+  unmodified against the reference's headers by oracle/build_ref_tests.sh and linked with OUR library
+  (oracle/_ref/bin/ours/) and with the reference library (oracle/_ref/bin/ref/): both must run and print the same
+  error column (the programs compare the GPU result with a LAPACK loop on the host).
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests import _util as U
+
+CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+BIN = os.path.join(U.ORACLE_DIR, "_ref", "bin")
+
+
+def _build_link_compat(tmpdir):
+    kb = U.kblas()
+    exe = os.path.join(str(tmpdir), "link_compat")
+    libdir = os.path.dirname(kb.LIB_PATH)
+    cmd = ["g++", "-O1", "-std=c++14", "-I" + os.path.join(U.ROOT, "include"), "-I" + os.path.join(CUDA, "include"),
+           os.path.join(U.ROOT, "tests", "cpp", "link_compat.cpp"), "-o", exe, "-L" + libdir, "-l:libkblas-gpu.so",
+           "-L" + os.path.join(CUDA, "lib64"), "-lcudart", "-Wl,-rpath," + libdir, "-Wl,--no-undefined"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_cpp_translation_unit_compiles_and_links(built, tmp_path):
+    exe = _build_link_compat(tmp_path)
+    out = subprocess.check_output([exe], text=True)      # no argument: resolves the symbols, touches no GPU
+    assert "symbols resolved" in out and "kblas_roundup(33,32)=64" in out and "CLOSEST_REG_SIZE(24)=16" in out
+
+
+def test_reference_test_programs_link_against_our_library(built):
+    """CPU: the eight reference programs exist and their dynamic dependency is OUR library (not the reference's)."""
+    if not os.path.isdir(os.path.join(BIN, "ours")):
+        pytest.skip("oracle/_ref/bin not built (needs /root/reference at build time)")
+    for op in ("potrf", "trsm", "potrs", "posv"):
+        for p in "sd":
+            exe = os.path.join(BIN, "ours", f"test_{p}{op}_batch")
+            assert os.path.exists(exe), exe
+            dyn = subprocess.check_output(["readelf", "-d", exe], text=True)
+            assert "libkblas-gpu.so" in dyn and "libkblas_ref.so" not in dyn
+            undefined = subprocess.check_output(["nm", "-uC", exe], text=True)
+            assert "kblasCreate" in undefined        # resolved at load time from libkblas-gpu.so
+
+
+@pytest.mark.gpu
+def test_cpp_translation_unit_runs_on_gpu(tmp_path):
+    exe = _build_link_compat(tmp_path)
+    r = subprocess.run([exe, "run"], text=True, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MISMATCH" not in r.stdout and "all offset entry points agree" in r.stdout
+
+
+def _rows(text):
+    """data rows of a reference test program's table: lines that start with a number (batch count / size columns)"""
+    rows = []
+    for line in text.splitlines():
+        f = line.split()
+        if len(f) >= 5 and re.fullmatch(r"\d+", f[0]):
+            rows.append(f)
+    return rows
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", ["potrf", "trsm", "potrs", "posv"])
+@pytest.mark.parametrize("p", ["d", "s"])
+def test_reference_test_programs_run_against_our_library(op, p):
+    """the reference's own bench binaries, unmodified, on OUR library: they run to completion, and the error they
+    print against their host LAPACK loop is as small as with the reference library itself"""
+    if not os.path.isdir(os.path.join(BIN, "ours")):
+        pytest.skip("oracle/_ref/bin not built (needs /root/reference at build time)")
+    args = ["-N", "32", "--batch", "200", "-c", "--nruns", "2"]
+    if op in ("trsm", "potrs", "posv"):
+        args += ["-SR"]
+    outs = {}
+    for who in ("ours", "ref"):
+        for strided in ([], ["-s"]):
+            r = subprocess.run([os.path.join(BIN, who, f"test_{p}{op}_batch")] + args + strided, text=True,
+                               capture_output=True, timeout=600)
+            assert r.returncode == 0, (who, r.stdout[-2000:], r.stderr[-2000:])
+            outs[(who, bool(strided))] = r.stdout
+    eps = U.EPS[{"d": __import__("numpy").float64, "s": __import__("numpy").float32}[p]]
+    for strided in (False, True):
+        mine, theirs = _rows(outs[("ours", strided)]), _rows(outs[("ref", strided)])
+        assert mine and len(mine) == len(theirs), (outs[("ours", strided)], outs[("ref", strided)])
+        for a, b in zip(mine, theirs):
+            err_a, err_b = float(a[-1]), float(b[-1])       # last column: error vs the host LAPACK loop
+            assert err_a == err_a and err_a <= max(100 * 32 * eps, 10 * err_b), (a, b)
