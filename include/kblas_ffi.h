@@ -114,4 +114,29 @@ int kblasxSpotrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, cons
 int kblasxDpotrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const double *A_in, double *A_out,
                                     int lda, long strideA, int batchCount, int *info_host);
 
+
+/* (5) packed lower-triangular batch layout: no reference counterpart (the reference's nearest routine
+ *     is the pivoted batch_pstrf on full storage, include/batch_pstrf.h).  Matrix b is stored as LAPACK ?pptrf takes it
+ *     for uplo = 'L':  AP_b[ j*n - j(j-1)/2 + (i-j) ] = A_b(i,j), i >= j;  n(n+1)/2 elements, matrix b at AP + b*strideAP
+ *     (strideAP >= n(n+1)/2) or AP_array[b].  Physical bytes == algorithmic bytes: a 32 x 32 fp64 matrix moves 8448 B
+ *     instead of the 12288 B of DRAM lines the column-major layout costs.  n <= 32; same contract as
+ *     kblas?potrf_batch otherwise (Lower only, info untouched unless KBLAS_B200_INFO_MODE=lapack, async on the handle's
+ *     stream, empty batch -> KBLAS_UnknownError).  For n % 8 == 0 the factor is bit-identical to kblas?potrf_batch's.
+ *     The TMA-staged fast path needs 16-byte aligned matrices (AP and strideAP*sizeof(T) multiples of 16). */
+int kblasxSpptrf_batch_strided(kblasHandle_t handle, char uplo, int n, float *AP, long strideAP, int batchCount,
+                               int *info_array);
+int kblasxDpptrf_batch_strided(kblasHandle_t handle, char uplo, int n, double *AP, long strideAP, int batchCount,
+                               int *info_array);
+int kblasxSpptrf_batch(kblasHandle_t handle, char uplo, int n, float **AP_array, int batchCount, int *info_array);
+int kblasxDpptrf_batch(kblasHandle_t handle, char uplo, int n, double **AP_array, int batchCount, int *info_array);
+/* lower triangle of column-major A (lda, strideA) -> packed AP, and back (unpack writes ONLY the lower triangle of A) */
+int kblasxStri_pack_batch_strided(kblasHandle_t handle, char uplo, int n, const float *A, int lda, long strideA,
+                                  float *AP, long strideAP, int batchCount);
+int kblasxDtri_pack_batch_strided(kblasHandle_t handle, char uplo, int n, const double *A, int lda, long strideA,
+                                  double *AP, long strideAP, int batchCount);
+int kblasxStri_unpack_batch_strided(kblasHandle_t handle, char uplo, int n, const float *AP, long strideAP,
+                                    float *A, int lda, long strideA, int batchCount);
+int kblasxDtri_unpack_batch_strided(kblasHandle_t handle, char uplo, int n, const double *AP, long strideAP,
+                                    double *A, int lda, long strideA, int batchCount);
+
 #endif /* KBLAS_B200_FFI_H */

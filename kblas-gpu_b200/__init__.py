@@ -92,6 +92,10 @@ _sig("kblasx_reg_size", _i, _i)
 _sig("kblasx_closest_reg_size", _i, _i)
 for _p, _t in (("S", C.c_float), ("D", C.c_double)):
     _sig(f"kblasx{_p}potrf_batch_strided_host", _i, _H, _c, _i, _P, _P, _i, _l, _i, _P)
+    _sig(f"kblasx{_p}pptrf_batch_strided", _i, _H, _c, _i, _P, _l, _i, _P)
+    _sig(f"kblasx{_p}pptrf_batch", _i, _H, _c, _i, _P, _i, _P)
+    _sig(f"kblasx{_p}tri_pack_batch_strided", _i, _H, _c, _i, _P, _i, _l, _P, _l, _i)
+    _sig(f"kblasx{_p}tri_unpack_batch_strided", _i, _H, _c, _i, _P, _l, _P, _i, _l, _i)
     _sig(f"kblas{_p}potrf_batch", _i, _H, _c, _i, _P, _i, _i, _P)
     _sig(f"kblas{_p}potrf_batch_strided", _i, _H, _c, _i, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}trsm_batch", _i, _H, _c, _c, _c, _c, _i, _i, _t, _P, _i, _P, _i, _i)
@@ -305,6 +309,24 @@ class Handle:
         A_in's storage (padding included) with the lower triangles replaced by the factors."""
         f = getattr(_lib, f"kblasx{_prec(A_in, prec)}potrf_batch_strided_host")
         return f(self._h, _ch(uplo), n, _hptr(A_in), _hptr(A_out), lda, strideA, batch, _hptr(info))
+
+    # -- compute: packed lower-triangular layout (LAPACK ?pptrf storage); no reference counterpart ------
+    def pptrf_batch_strided(self, uplo, n, AP, strideAP, batch, info=None, prec=None):
+        """Cholesky of `batch` matrices stored packed-lower: AP[b*strideAP + j*n - j(j-1)/2 + (i-j)] = A_b(i,j), i >= j"""
+        f = getattr(_lib, f"kblasx{_prec(AP, prec)}pptrf_batch_strided")
+        return f(self._h, _ch(uplo), n, _ptr(AP), strideAP, batch, _ptr(info))
+
+    def pptrf_batch(self, uplo, n, AP_array, batch, info=None, prec="D"):
+        f = getattr(_lib, f"kblasx{prec.upper()}pptrf_batch")
+        return f(self._h, _ch(uplo), n, _ptr(AP_array), batch, _ptr(info))
+
+    def tri_pack_batch_strided(self, uplo, n, A, lda, strideA, AP, strideAP, batch, prec=None):
+        f = getattr(_lib, f"kblasx{_prec(A, prec)}tri_pack_batch_strided")
+        return f(self._h, _ch(uplo), n, _ptr(A), lda, strideA, _ptr(AP), strideAP, batch)
+
+    def tri_unpack_batch_strided(self, uplo, n, AP, strideAP, A, lda, strideA, batch, prec=None):
+        f = getattr(_lib, f"kblasx{_prec(A, prec)}tri_unpack_batch_strided")
+        return f(self._h, _ch(uplo), n, _ptr(AP), strideAP, _ptr(A), lda, strideA, batch)
 
     # -- compute: pointer arrays (device arrays of device pointers) -----------------------
     def potrf_batch(self, uplo, n, A_array, lda, batch, info=None, prec="D"):

@@ -259,6 +259,32 @@ int ORA_(oracle_posv_batch_strided)(char side, char uplo, int m, int n, ORA_T *A
   return 1;
 }
 
+/* ---- packed lower storage (LAPACK ?pptrf, uplo = 'L'): AP[j*n - j(j-1)/2 + (i-j)] = A(i,j), i >= j.
+ * The reference has no packed batch routine (its batch_pstrf, src/batch_svd/batch_pstrf.cu:226-246,
+ * is pivoted Cholesky on full storage), so the oracle for kblasx?pptrf_batch is DEFINED as: unpack, factor with the
+ * restated reference potrf above (same recursion and roundings, Xpotrf_batch_drivers.cuh:30-137), re-pack.  Parity
+ * anchor: pptrf(pack(A)) == pack(potrf(A)) with potrf pinned by the reference's golden vectors. */
+int ORA_(oracle_pptrf_batch_strided)(char uplo, int n, ORA_T *AP, long strideAP, int batchCount) {
+  if (uplo != 'L' && uplo != 'l') return -2; /* KBLAS_NotImplemented */
+  if (n <= 0) return 1;
+  if (n > 256) return -2;
+  static ORA_T W[256 * 256];
+  const int lda = n;
+  for (long b = 0; b < batchCount; b++) {
+    ORA_T *P = AP + b * strideAP;
+    ORA_T *A = W;
+    size_t e = 0;
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) A_(i, j) = (i >= j) ? P[e++] : (ORA_T)0;
+    ORA_(potrf)(n, A, lda);
+    e = 0;
+    for (int j = 0; j < n; j++)
+      for (int i = j; i < n; i++) P[e++] = A_(i, j);
+  }
+  return 1;
+}
+
+
 #undef A_
 #undef B_
 #undef C_

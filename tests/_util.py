@@ -51,6 +51,7 @@ def oracle():
             getattr(_oracle, f"oracle_trsm_batch_strided_{s}").argtypes = [c, c, c, c, i, i, t, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_potrs_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_posv_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
+            getattr(_oracle, f"oracle_pptrf_batch_strided_{s}").argtypes = [c, i, P, l, i]
     return _oracle
 
 
@@ -72,6 +73,13 @@ def oracle_potrf(A, n, uplo="L"):
     b, nc, lda = A.shape
     f = getattr(oracle(), f"oracle_potrf_batch_strided_{SUFFIX[_dt(A)]}")
     return f(uplo.encode(), n, _np_ptr(A), lda, nc * lda, b)
+
+
+def oracle_pptrf(AP, n, uplo="L"):
+    """in place on AP[(batch, strideAP)]: packed lower storage, oracle/kblas_oracle_impl.h oracle_pptrf_batch_strided"""
+    b, stride = AP.shape
+    f = getattr(oracle(), f"oracle_pptrf_batch_strided_{SUFFIX[_dt(AP)]}")
+    return f(uplo.encode(), n, _np_ptr(AP), stride, b)
 
 
 def oracle_trsm(side, uplo, trans, diag, m, n, alpha, A, B):
@@ -155,6 +163,28 @@ def as_mats(A, rows, cols):
 
 def lower(M):
     return np.tril(M)
+
+
+def pack_lower(A, n):
+    """(batch, ncols, ld) strided layout -> (batch, n(n+1)/2): LAPACK packed lower, column by column (rows j..n-1 of
+    column j) -- the layout of kblasx?pptrf_batch and of the large golden factors"""
+    return np.concatenate([A[:, j, j:n] for j in range(n)], axis=1).copy()
+
+
+def unpack_lower(P, n, dtype=None):
+    """inverse of pack_lower into a zero-filled (batch, n, n) strided array (lda = n)"""
+    out = np.zeros((P.shape[0], n, n), dtype=dtype or P.dtype)
+    o = 0
+    for j in range(n):
+        out[:, j, j:n] = P[:, o:o + n - j]
+        o += n - j
+    return out
+
+
+def sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def potrf_residual(A0, Lf, n):

@@ -14,7 +14,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from tests._util import RefLib, rand_batch, rand_spd_batch  # noqa: E402
+from tests._util import RefLib, as_mats, pack_lower, rand_batch, rand_spd_batch, sha  # noqa: E402
 
 INFO_SENTINEL = 77
 
@@ -45,6 +45,8 @@ def main(outdir):
         posv_p = ref.fn(f"kblas{p}posv_batch", [H, c, c, i, i, P, i, P, i, i, P])
 
         # ---- strided potrf / posv at the config-4 sizes ----------------------------------------
+        # (large: the input is stored as its generator seed + a SHA-256 of the bytes, the factor as its packed
+        #  lower triangle -- tests regenerate the input with tests/_util.rand_spd_batch and verify the hash)
         for n in (128, 256):
             batch = 1
             A = rand_spd_batch(batch, n, dtype=dt, seed=900 + n)
@@ -54,7 +56,10 @@ def main(outdir):
             ref.allocate()
             rc = potrf_s(ref.h, b"L", n, dA.data_ptr(), n, n * n, batch, info.data_ptr())
             torch.cuda.synchronize()
-            cases[f"potrf_{p}_n{n}_lda{n}"] = dict(A_in=A, A_out=dA.cpu().numpy(), rc=rc, info=info.cpu().numpy())
+            out = dA.cpu().numpy()
+            assert np.array_equal(np.triu(as_mats(out, n, n), 1), np.triu(as_mats(A, n, n), 1))
+            cases[f"potrfbig_{p}_n{n}"] = dict(seed=900 + n, A_in_sha256=sha(A), L_out_packed=pack_lower(out, n), rc=rc,
+                                               info=info.cpu().numpy())
         m, n, batch = 16, 256, 1
         A = rand_spd_batch(batch, n, dtype=dt, seed=950)
         B = rand_batch(batch, m, n, dtype=dt, seed=951)
@@ -64,12 +69,13 @@ def main(outdir):
         ref.allocate()
         rc = posv_s(ref.h, b"R", b"L", m, n, dA.data_ptr(), n, n * n, dB.data_ptr(), m, m * n, batch, info.data_ptr())
         torch.cuda.synchronize()
-        cases[f"posv_{p}_m{m}_n{n}"] = dict(A_in=A, B_in=B, A_out=dA.cpu().numpy(), B_out=dB.cpu().numpy(), rc=rc,
-                                            info=info.cpu().numpy())
+        cases[f"posvbig_{p}_m{m}_n{n}"] = dict(seed_A=950, seed_B=951, A_in_sha256=sha(A), B_in=B,
+                                               L_out_packed=pack_lower(dA.cpu().numpy(), n), B_out=dB.cpu().numpy(), rc=rc,
+                                               info=info.cpu().numpy())
 
         # ---- pointer-array entry points -----------------------------------------------------------
-        for n in (8, 16, 24, 32, 48, 64):
-            batch, m = 7, 16
+        for n in (8, 16, 32, 64):
+            batch, m = 3, 16
             perm = np.random.default_rng(n).permutation(batch)
             A = rand_spd_batch(batch, n, dtype=dt, seed=1000 + n)
             B = rand_batch(batch, m, n, dtype=dt, seed=1100 + n)
@@ -83,19 +89,21 @@ def main(outdir):
             rc = potrf_p(ref.h, b"L", n, pa.data_ptr(), n, batch, info.data_ptr())
             torch.cuda.synchronize()
             L = dA.cpu().numpy()
-            cases[f"potrfptr_{p}_n{n}"] = dict(A_in=A, A_out=L, rc=rc, info=info.cpu().numpy(), perm=perm)
-            # potrs with that factor
+            key = f"potrfptr_{p}_n{n}"
+            cases[key] = dict(A_in=A, A_out=L, rc=rc, info=info.cpu().numpy(), perm=perm)
+            # potrs with that factor (stored once: L_from names the case whose A_out is the factor)
             dB = dev_of(B)
             pb = ptrs(dB, perm, m * n, es)
             rc = potrs_p(ref.h, b"R", b"L", m, n, pa.data_ptr(), n, pb.data_ptr(), m, batch)
             torch.cuda.synchronize()
-            cases[f"potrsptr_{p}_m{m}_n{n}"] = dict(L_in=L, B_in=B, B_out=dB.cpu().numpy(), rc=rc, perm=perm)
-            # posv from A
+            cases[f"potrsptr_{p}_m{m}_n{n}"] = dict(L_from=key, B_in=B, B_out=dB.cpu().numpy(), rc=rc, perm=perm)
+            # posv from A (A_from names the case whose A_in is the input; its factor equals that case's A_out)
             dA2, dB2 = dev_of(A), dev_of(B)
             pa2, pb2 = ptrs(dA2, perm, n * n, es), ptrs(dB2, perm, m * n, es)
             rc = posv_p(ref.h, b"R", b"L", m, n, pa2.data_ptr(), n, pb2.data_ptr(), m, batch, info.data_ptr())
             torch.cuda.synchronize()
-            cases[f"posvptr_{p}_m{m}_n{n}"] = dict(A_in=A, B_in=B, A_out=dA2.cpu().numpy(), B_out=dB2.cpu().numpy(), rc=rc,
+            assert np.array_equal(dA2.cpu().numpy(), L), "posv's factor differs from potrf's"
+            cases[f"posvptr_{p}_m{m}_n{n}"] = dict(A_from=key, B_in=B, B_out=dB2.cpu().numpy(), rc=rc,
                                                    info=info.cpu().numpy(), perm=perm)
             # trsm, four variants, on the factor
             for side in "LR":
@@ -107,7 +115,7 @@ def main(outdir):
                     rc = trsm_p(ref.h, side.encode(), b"L", trans.encode(), b"N", mm, nn, 0.28, pa.data_ptr(), n,
                                 pbt.data_ptr(), mm, batch)
                     torch.cuda.synchronize()
-                    cases[f"trsmptr_{p}_{side}{trans}_m{mm}_n{nn}"] = dict(A_in=L, B_in=Bt, B_out=dBt.cpu().numpy(), rc=rc,
+                    cases[f"trsmptr_{p}_{side}{trans}_m{mm}_n{nn}"] = dict(L_from=key, B_in=Bt, B_out=dBt.cpu().numpy(), rc=rc,
                                                                           alpha=0.28, perm=perm)
 
         # ---- alpha == 0 (documents what the reference does; strided) ---------------------------------
