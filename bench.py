@@ -166,7 +166,7 @@ def make_spd(torch, batch, n, dtype, seed):
     Built in slices to bound the transient memory."""
     out = torch.empty((batch, n, n), device="cuda", dtype=dtype)
     g = torch.Generator(device="cuda").manual_seed(seed)
-    step = 1 << 18
+    step = max(1, (1 << 28) // (n * n))   # <= 2^28 elements per slice whatever n is
     for lo in range(0, batch, step):
         hi = min(batch, lo + step)
         a = torch.rand((hi - lo, n, n), generator=g, device="cuda", dtype=dtype)
@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the total batch (default 2^20 at N=1, 2^23 at N>1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sweep over the other BASELINE configurations (N = 1 only)")
     args = ap.parse_args()
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -375,8 +376,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     total_batch = args.batch or (world << 20)
-    slab = importlib.import_module("kblas-gpu_b200.slab")
-    b0, b1 = slab.slab_range(total_batch, world, rank)
+    if args.impl == "ours":
+        b0, b1 = importlib.import_module("kblas-gpu_b200.slab").slab_range(total_batch, world, rank)
+    else:
+        # the reference arms must not map libkblas-gpu.so: same ceil-sized contiguous slabs, computed here
+        per = -(-total_batch // world)
+        b0 = min(total_batch, rank * per)
+        b1 = min(total_batch, b0 + per)
     batch = b1 - b0
 
     impl = None
@@ -485,6 +491,16 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(torch, dist, impl, n, batch, total_batch, pristine, rank)
 
+    # ---- the other BASELINE configurations + the packed layout (rank 0, N = 1, default batch only) --------------
+    configs, fp64_peak = None, None
+    if rank == 0 and world == 1 and args.impl == "ours" and not args.no_configs and not args.batch:
+        del bufs, pristine
+        torch.cuda.empty_cache()
+        try:
+            configs, fp64_peak = run_configs(torch, impl.kb, impl.h, peak, peak_src)
+        except Exception as e:   # the sweep must never cost the headline line
+            configs = [{"error": str(e)[:300]}]
+
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -510,6 +526,9 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if configs is not None:
+            line["configs"] = configs
+            line["fp64_peak_tflops_measured"] = fp64_peak
         if args.impl == "reference-gpu":
             line["impl"] = "reference"
             line["reference_kind"] = "unmodified KBLAS-GPU sources compiled for sm_100 (oracle/_ref/libkblas_ref.so)"
@@ -522,6 +541,145 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _median_ms(torch, fn, restore, reps):
+    ts = []
+    for _ in range(reps):
+        restore()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def measure_fp64_peak(torch):
+    """FP64 pipe peak of THIS box the way MEASURED_PEAKS.json measures its bf16 peak: a library GEMM (torch.matmul
+    fp64 4096^3, 2 N^3 flop), best of 5 -- the denominator for the FP64-bound configurations (n >= 128)"""
+    N = 4096
+    a = torch.rand((N, N), device="cuda", dtype=torch.float64)
+    b = torch.rand((N, N), device="cuda", dtype=torch.float64)
+    torch.matmul(a, b)
+    best = None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * N ** 3 / (best * 1e-3) / 1e12
+
+
+def run_configs(torch, kb, h, peak_hbm, peak_src, reps=5):
+    """Every BASELINE.json configuration beside the headline one, each timed on ITS OWN stated size with CUDA events
+    (median of `reps`, inputs larger than L2 restored from a pristine copy outside the timed region) and reported
+    against the roofline that bounds it with the algorithmic bytes / flops of SURVEY.md §8(d):
+      potrf  n(n+1) es            trsm / potrs  (k(k+1)/2 + 2mn) es          posv  (n(n+1) + 2mn) es
+      FLOPS_POTRF = n^3/3 + n^2/2 + n/6, FLOPS_TRSM = n m^2, FLOPS_POTRS = 2 m n^2 (testing/flops.h:74-130)
+    plus the packed-layout entry points (kblasx?pptrf_batch_strided).  Rank 0, N = 1 only."""
+    out = []
+    fp64_peak = measure_fp64_peak(torch)
+    fp32_peak = None   # fp32 configurations here are all HBM-bound
+
+    def entry(name, op, n, batch, es, ms_med, ms_best, algo_bytes, flops, kernel, extra=None):
+        gbs = batch * algo_bytes / (ms_med * 1e-3) / 1e9
+        tfl = batch * flops / (ms_med * 1e-3) / 1e12
+        t_hbm = algo_bytes / (peak_hbm * 1e9)
+        t_fp = flops / (fp64_peak * 1e12) if es == 8 else 0.0
+        if t_fp > t_hbm:
+            roof = {"bound": "fp64", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak,
+                    "peak_source": "torch.matmul fp64 4096^3 on this box, best of 5 (measured in this run)",
+                    "frac_hbm": gbs / peak_hbm}
+        else:
+            roof = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "peak_source": peak_src}
+        roof.update({"traffic": None, "algorithmic_bytes_per_unit": algo_bytes, "flops_per_unit": flops, "units_per_launch": batch,
+                     "frac_best": roof["frac"] * ms_med / ms_best})
+        e = {"name": name, "op": op, "n": n, "batch": batch, "dtype": "f64" if es == 8 else "f32", "ms_median": ms_med,
+             "ms_best": ms_best, "value": batch / (ms_med * 1e-3), "unit": "problems/s", "gflops": tfl * 1e3, "kernel": kernel,
+             "roofline": roof}
+        if extra:
+            e.update(extra)
+        out.append(e)
+        log(f"[configs] {name}: {ms_med:.3f} ms, frac {roof['frac']:.3f} ({roof['bound']})")
+
+    potrf_fl = lambda n: n ** 3 / 3 + n ** 2 / 2 + n / 6
+    batch = 1 << 20
+    # ---- config 2: strided dpotrf + dpotrs, n sweep, batch 2^20 (m = n right-hand-side rows) -------------------
+    for n in (8, 16, 24, 32):
+        P = make_spd(torch, batch, n, torch.float64, 1)
+        A = torch.empty_like(P)
+        h.posv_batch_strided_wsquery("R", n, n, batch)
+        h.allocate_workspace()
+        med, best = _median_ms(torch, lambda: h.potrf_batch_strided("L", n, A, n, n * n, batch, None), lambda: A.copy_(P), reps)
+        entry(f"config2 dpotrf_batch_strided n={n}", "potrf", n, batch, 8, med, best, n * (n + 1) * 8, potrf_fl(n), h.last_kernel)
+        B0 = torch.rand((batch, n, n), device="cuda", dtype=torch.float64)
+        B = torch.empty_like(B0)
+        med, best = _median_ms(torch, lambda: h.potrs_batch_strided("R", "L", n, n, A, n, n * n, B, n, n * n, batch), lambda: B.copy_(B0), reps)
+        entry(f"config2 dpotrs_batch_strided n={n} m={n}", "potrs", n, batch, 8, med, best, (n * (n + 1) // 2 + 2 * n * n) * 8,
+              2.0 * n * n * n, h.last_kernel)
+        # packed layout (physical bytes == algorithmic bytes)
+        sz = n * (n + 1) // 2
+        PP0 = torch.empty((batch, sz), device="cuda", dtype=torch.float64)
+        h.tri_pack_batch_strided("L", n, P, n, n * n, PP0, sz, batch)
+        PP = torch.empty_like(PP0)
+        med, best = _median_ms(torch, lambda: h.pptrf_batch_strided("L", n, PP, sz, batch, None), lambda: PP.copy_(PP0), reps)
+        entry(f"packed dpptrf_batch_strided n={n}", "pptrf", n, batch, 8, med, best, n * (n + 1) * 8, potrf_fl(n), h.last_kernel,
+              {"layout": "LAPACK packed lower, stride n(n+1)/2 (kblasx entry point, no reference counterpart)"})
+        del P, A, B0, B, PP0, PP
+    # ---- config 3: strided trsm side L, uplo L, n = 32, nrhs = 32, batch 2^20, fp32 and fp64 -------------------
+    n = 32
+    for prec, tdt, es in (("d", torch.float64, 8), ("s", torch.float32, 4)):
+        L = make_spd(torch, batch, n, tdt, 2)
+        h.potrf_batch_strided("L", n, L, n, n * n, batch, None)
+        B0 = torch.rand((batch, n, n), device="cuda", dtype=tdt)
+        B = torch.empty_like(B0)
+        h.trsm_batch_strided_wsquery("L", n, n, batch)
+        h.allocate_workspace()
+        for trans in ("N", "T"):
+            med, best = _median_ms(torch, lambda: h.trsm_batch_strided("L", "L", trans, "N", n, n, 0.28, L, n, n * n, B, n, n * n, batch),
+                                   lambda: B.copy_(B0), reps)
+            entry(f"config3 {prec}trsm_batch_strided L,L,{trans} m=n=32", "trsm", n, batch, es, med, best,
+                  (n * (n + 1) // 2 + 2 * n * n) * es, float(n * n * n), h.last_kernel)
+        if prec == "s":
+            P = L  # reuse the allocation: spotrf on fresh data
+            P.copy_(make_spd(torch, batch, n, tdt, 3))
+            W = torch.empty_like(P)
+            med, best = _median_ms(torch, lambda: h.potrf_batch_strided("L", n, W, n, n * n, batch, None), lambda: W.copy_(P), reps)
+            entry("spotrf_batch_strided n=32", "potrf", n, batch, 4, med, best, n * (n + 1) * 4, potrf_fl(n), h.last_kernel)
+            del W
+        del L, B0, B
+    # ---- config 4: pointer-array dposv, n = 64 / 128 / 256, 16 right-hand-side rows, batch 64K -----------------
+    m, b4 = 16, 1 << 16
+    for n in (64, 128, 256):
+        P = make_spd(torch, b4, n, torch.float64, 4)
+        A = torch.empty_like(P)
+        B0 = torch.rand((b4, n, m), device="cuda", dtype=torch.float64)
+        B = torch.empty_like(B0)
+        perm = torch.randperm(b4, device="cuda")
+        pa = (A.data_ptr() + perm * (n * n * 8)).contiguous()
+        pb = (B.data_ptr() + perm * (m * n * 8)).contiguous()
+        h.posv_batch_wsquery("R", m, n, b4)
+        h.allocate_workspace()
+
+        def restore():
+            A.copy_(P)
+            B.copy_(B0)
+        lc0 = h.launch_count
+        med, best = _median_ms(torch, lambda: h.posv_batch("R", "L", m, n, pa, n, pb, m, b4, None, prec="D"), restore, 3)
+        nl = (h.launch_count - lc0) // 3
+        entry(f"config4 dposv_batch (pointer array) n={n} m=16", "posv", n, b4, 8, med, best, (n * (n + 1) + 2 * m * n) * 8,
+              potrf_fl(n) + 2.0 * m * n * n, h.last_kernel, {"launches_per_call": nl})
+        med, best = _median_ms(torch, lambda: h.potrf_batch("L", n, pa, n, b4, None, prec="D"), restore, 3)
+        entry(f"config4 dpotrf_batch (pointer array) n={n}", "potrf", n, b4, 8, med, best, n * (n + 1) * 8, potrf_fl(n), h.last_kernel)
+        del P, A, B0, B
+    return out, fp64_peak
 
 
 def run_e2e(torch, dist, impl, n, batch, total_batch, pristine, rank, steps=3, warmup=1):

@@ -102,18 +102,18 @@ potrf_packed_kernel(BatchRef<T, STRIDED> APref, const int batchCount) {
   constexpr int ES = (int)sizeof(T);
   typedef typename Vec2T<T>::type V2;
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_pk[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int l = lane % G;
   const int g = lane / G;
-  T *const wsm = reinterpret_cast<T *>(smem_raw + (size_t)warp * Sm::per_warp_bytes);
+  T *const wsm = reinterpret_cast<T *>(smem_pk + (size_t)warp * Sm::per_warp_bytes);
   T *const wbase = wsm + (g / GH) * ((NP / 2) * PAIR) + (g % GH) * 2;  // broadcast line, as in potrf_small.cuh
   T *const in_w = wsm + Sm::BC;
   T *const out_w = in_w + Sm::IN;
   const T *const in_g = in_w + g * Geo::STRIDE;
   T *const out_g = out_w + g * Geo::OSTRIDE;
-  const uint32_t bar = smem_u32(smem_raw + (size_t)WARPS * Sm::per_warp_bytes) + 8 * warp;
+  const uint32_t bar = smem_u32(smem_pk + (size_t)WARPS * Sm::per_warp_bytes) + 8 * warp;
   uint32_t parity = 0;
 
   const long nwb = ((long)batchCount + MPW - 1) / MPW;
@@ -356,6 +356,81 @@ potrf_packed_generic_kernel(const int n, BatchRef<T, STRIDED> APref, const int b
     if (info_mode && active && l == 0) info[mat] = bad;
     __syncwarp();
 #undef KX_IDX
+  }
+}
+
+// ---- n = 8 (and fp32 n = 16): ONE LANE PER MATRIX ------------------------------------------------------------------
+// The 8-lanes-per-matrix mapping above spends its time on cross-lane traffic when a matrix is only 36 values
+// (ncu, round 1: shared-memory data pipe 87 % busy at n = 8).  Here a warp owns 32 consecutive packed matrices --
+// 32*SZ contiguous elements when strideAP == SZ -- and
+//   1. reads them with fully coalesced loads (flat element f = k*32 + lane, k = 0..SZ-1),
+//   2. transposes through shared memory with one element of padding per matrix (stride SZ+1: odd word stride,
+//      conflict-free both ways) so that lane m ends up with all SZ values of matrix m in registers,
+//   3. factors with no cross-lane traffic at all (fully unrolled, same recurrence: d = a_jj, r = rsqrt(d),
+//      column *= r, a_ik -= l_ij l_kj),
+//   4. transposes back and stores coalesced.
+// Requires strideAP == SZ (contiguous batch); other strides take the generic kernel.
+template <typename T, int N, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+potrf_packed_lane_kernel(T *__restrict__ AP, const int batchCount) {
+  constexpr int SZ = packed_size(N);
+  constexpr int LD = SZ + 1;  // padded per-matrix stride in shared memory
+  extern __shared__ __align__(128) unsigned char smem_pk[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T *const sm = reinterpret_cast<T *>(smem_pk) + (size_t)warp * 32 * LD;
+  const long nwb = ((long)batchCount + 31) / 32;
+  for (long wb = (long)blockIdx.x * WARPS + warp; wb < nwb; wb += (long)gridDim.x * WARPS) {
+    T *base = AP + wb * 32 * SZ;
+    const long rem = (long)batchCount - wb * 32;
+    const int cnt = rem < 32 ? (int)rem : 32;      // matrices in this warp-batch
+    const int total = cnt * SZ;                    // valid flat elements
+    T v[SZ];
+#pragma unroll
+    for (int k = 0; k < SZ; ++k) {
+      const int f = k * 32 + lane;
+      v[k] = T(0);
+      ldg_stream_if(v[k], base + f, f < total);
+    }
+#pragma unroll
+    for (int k = 0; k < SZ; ++k) {
+      const int f = k * 32 + lane;
+      sm[f + f / SZ] = v[k];                       // matrix f / SZ, element f % SZ -> (f / SZ) * LD + f % SZ
+    }
+    __syncwarp();
+    T a[SZ];
+#pragma unroll
+    for (int e = 0; e < SZ; ++e) a[e] = sm[lane * LD + e];
+    if (lane >= cnt) {                             // tail lanes factor the identity (finite arithmetic, never stored)
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j; i < N; ++i) a[packed_col_off(N, j) + i - j] = (i == j) ? T(1) : T(0);
+    }
+#define KX_P(i_, j_) a[packed_col_off(N, (j_)) + (i_) - (j_)]
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const T r = rsqrt_t(KX_P(j, j));
+#pragma unroll
+      for (int i = j; i < N; ++i) KX_P(i, j) *= r;
+#pragma unroll
+      for (int k = j + 1; k < N; ++k) {
+        const T nk = -KX_P(k, j);
+#pragma unroll
+        for (int i = k; i < N; ++i) KX_P(i, k) = fma_t(KX_P(i, j), nk, KX_P(i, k));
+      }
+    }
+#undef KX_P
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < SZ; ++e) sm[lane * LD + e] = a[e];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SZ; ++k) {
+      const int f = k * 32 + lane;
+      stg_stream_if(base + f, sm[f + f / SZ], f < total);
+    }
+    __syncwarp();
   }
 }
 

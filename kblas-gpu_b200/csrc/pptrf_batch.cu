@@ -42,18 +42,39 @@ static int launch_packed_generic(KBlasHandle *h, const char *name, int n, BatchR
   return KBLAS_Success;
 }
 
-// variant_override (env KBLAS_B200_VARIANT, A/B runs): 20 = plain loads + plain stores, 21 = bulk in + plain stores,
-// 22 = bulk in + bulk out, 23 = 22 without the per-batch CTA barrier; default = the measured best per size
+// n == N, contiguous batch (strideAP == N(N+1)/2): one lane per matrix (kernels/potrf_packed.cuh)
+template <typename T, int N, int WARPS, int MINB>
+static int launch_packed_lane(KBlasHandle *h, const char *name, T *AP, int batchCount) {
+  auto kern = potrf_packed_lane_kernel<T, N, WARPS, MINB>;
+  const size_t smem = (size_t)WARPS * 32 * (packed_size(N) + 1) * sizeof(T);
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  const long per_cta = (long)WARPS * 32;
+  const long need = (batchCount + per_cta - 1) / per_cta;
+  const long wave = (long)h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, MINB);
+  const long grid = need < wave ? need : wave;
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(AP, batchCount);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
+// variant_override (env KBLAS_B200_VARIANT, A/B runs): 20 = plain loads + plain stores, 21 = TMA bulk loads + plain
+// stores, 22 = TMA in + TMA out with the per-batch CTA barrier of potrf_reg_kernel; default = TMA in + TMA out, warps
+// free-running.  Measured on B200, 2^20 matrices, fraction of the measured HBM copy peak (profiles/r02_packed_variants.txt):
+//   fp64 n=32: 0.66 / 0.75 / 0.79 / 0.87     n=24: 0.70 / 0.81 / 0.87 / 0.93     n=16: 0.85 (default)
+//   fp32 n=32: 0.51 / 0.60 / 0.68 / 0.74     (kblas?potrf_batch_strided on full storage: fp64 0.68 / 0.59 / 0.61, fp32 0.46)
+#define KX_STR2(x) #x
+#define KX_STR(x) KX_STR2(x)
 #define KX_PK(NP, W, MB, IB, OB, LS, NAME) \
-  launch_packed<T, NP, W, MB, STRIDED, IB, OB, LS>(h, "potrf_packed<NP=" #NP ",W=" #W "," NAME ">", AP, batchCount)
+  launch_packed<T, NP, W, MB, STRIDED, IB, OB, LS>(h, NAME, AP, batchCount)
 
 template <typename T, int NP, int W, int MB, bool STRIDED>
 static int packed_exact(KBlasHandle *h, BatchRef<T, STRIDED> AP, int batchCount, bool aligned) {
   const int v = h->variant_override;
-  if (!aligned || v == 20) return KX_PK(NP, W, MB, false, false, true, "ldg,stg");
-  if (v == 21) return KX_PK(NP, W, MB, true, false, true, "tma-in,stg");
-  if (v == 23) return KX_PK(NP, W, MB, true, true, false, "tma-in,tma-out,free");
-  return KX_PK(NP, W, MB, true, true, true, "tma-in,tma-out");
+  if (!aligned || v == 20) return KX_PK(NP, W, MB, false, false, true, "potrf_packed<ldg,stg>");
+  if (v == 21) return KX_PK(NP, W, MB, true, false, true, "potrf_packed<tma-in,stg>");
+  if (v == 22) return KX_PK(NP, W, MB, true, true, true, "potrf_packed<tma-in,tma-out,lockstep>");
+  return KX_PK(NP, W, MB, true, true, false, "potrf_packed<tma-in,tma-out>");
 }
 
 template <typename T, bool STRIDED>
@@ -70,6 +91,16 @@ int pptrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> AP, 
   constexpr bool F32 = sizeof(T) == 4;
   const bool exact = (n % 8 == 0) && h->info_mode == KBLASX_INFO_COMPAT;
   if (exact) {
+    if constexpr (STRIDED) {
+      // tiny matrices, contiguous batch: one lane per matrix (any A/B override 20..24 selects the 8-lane kernels)
+      const bool ab = h->variant_override >= 20 && h->variant_override <= 24;
+      if (!ab && AP.stride == (long)packed_size(n)) {
+        if (n == 8) return launch_packed_lane<T, 8, 4, 4>(h, "potrf_packed_lane<N=8>", AP.base, batchCount);
+        if constexpr (F32) {
+          if (n == 16) return launch_packed_lane<T, 16, 4, 3>(h, "potrf_packed_lane<N=16>", AP.base, batchCount);
+        }
+      }
+    }
     if (n == 8) return packed_exact<T, 8, 4, 8, STRIDED>(h, AP, batchCount, aligned);
     if (n == 16) return packed_exact<T, 16, 4, 4, STRIDED>(h, AP, batchCount, aligned);
     if (n == 24) return packed_exact<T, 24, 4, 3, STRIDED>(h, AP, batchCount, aligned);

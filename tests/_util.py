@@ -247,3 +247,43 @@ class RefLib:
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+# --------------------------------------------------------------------------------------------
+# round-2 golden vectors (tests/golden/reference_gpu_r2.npz, made by tests/golden/make_golden_r2.py)
+
+def load_golden(fname):
+    path = os.path.join(GOLDEN_DIR, fname)
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/")
+        cases.setdefault(name, {})[field] = z[key]
+    return cases
+
+
+def golden_r2_inputs(cases, name):
+    """materialise the inputs of one round-2 case: large inputs are stored as (seed, SHA-256) and regenerated here,
+    factors shared between cases are stored once and referenced by name (L_from / A_from)"""
+    c = cases[name]
+    kind, p = name.split("_")[0], name.split("_")[1]
+    dt = np.float64 if p == "D" else np.float32
+    out = dict(c)
+    if kind == "potrfbig":
+        n = int(name.split("_n")[1])
+        A = rand_spd_batch(1, n, dtype=dt, seed=int(c["seed"]))
+        assert sha(A) == str(c["A_in_sha256"]), "numpy RNG stream changed: regenerate tests/golden/reference_gpu_r2.npz"
+        out["A_in"] = A
+    elif kind == "posvbig":
+        n = int(name.split("_n")[1])
+        A = rand_spd_batch(1, n, dtype=dt, seed=int(c["seed_A"]))
+        assert sha(A) == str(c["A_in_sha256"]), "numpy RNG stream changed: regenerate tests/golden/reference_gpu_r2.npz"
+        out["A_in"] = A
+    if "L_from" in c:
+        out["L_in"] = cases[str(c["L_from"])]["A_out"]
+    if "A_from" in c:
+        out["A_in"] = cases[str(c["A_from"])]["A_in"]
+        out["A_out"] = cases[str(c["A_from"])]["A_out"]
+    return out

@@ -602,6 +602,92 @@ def test_golden_vectors_through_the_c_abi(env):
     assert seen >= 80
 
 
+def test_golden_r2_vectors_through_the_c_abi(env):
+    """reference_gpu_r2.npz: config-4 sizes (n = 128 / 256) and the POINTER-ARRAY entry points of all four routines,
+    outputs of the unmodified reference library; pointer arrays rebuilt from the stored permutation."""
+    kb, h, torch = env
+    cases = U.load_golden("reference_gpu_r2.npz")
+    if cases is None:
+        pytest.skip("tests/golden/reference_gpu_r2.npz not generated yet")
+    seen = 0
+    for name in cases:
+        kind, p = name.split("_")[0], name.split("_")[1]
+        if kind == "trsmalpha0":
+            continue        # pinned in tests/test_oracle.py; our (different, documented) behaviour in test_trsm_alpha_zero_*
+        dt = DT[p]
+        es = np.dtype(dt).itemsize
+        eps = U.EPS[dt]
+        c = U.golden_r2_inputs(cases, name)
+
+        def ptr_array(d, elems):
+            return torch.from_numpy(d.data_ptr() + c["perm"].astype(np.int64) * elems * es).cuda()
+
+        if kind in ("potrfbig", "potrfptr"):
+            n = _num(name, "n")
+            batch = c["A_in"].shape[0]
+            dA = _dev(torch, c["A_in"])
+            info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+            if kind == "potrfbig":
+                h.potrf_batch_strided_wsquery(n, batch)
+                h.allocate_workspace()
+                rc = h.potrf_batch_strided("L", n, dA, n, n * n, batch, info)
+            else:
+                h.potrf_batch_wsquery(n, batch)
+                h.allocate_workspace()
+                rc = h.potrf_batch("L", n, ptr_array(dA, n * n), n, batch, info, prec=p)
+            torch.cuda.synchronize()
+            assert rc == int(c["rc"]) == 1, name
+            got = dA.cpu().numpy()
+            if kind == "potrfbig":
+                assert U.potrf_residual(c["A_in"], got, n) <= 10 * n * eps
+                assert np.abs(U.pack_lower(got, n) - c["L_out_packed"]).max() <= 100 * n * eps * np.abs(c["A_in"]).max(), name
+                assert np.array_equal(np.triu(U.as_mats(got, n, n), 1), np.triu(U.as_mats(c["A_in"], n, n), 1))
+            else:
+                _check_potrf(c["A_in"], got, n, dt, Lref=c["A_out"])
+            assert np.array_equal(info.cpu().numpy(), c["info"]), name
+        else:
+            m, n = _num(name, "m"), _num(name, "n")
+            batch = c["B_in"].shape[0]
+            dB = _dev(torch, c["B_in"])
+            if kind == "posvbig":
+                dA = _dev(torch, c["A_in"])
+                h.posv_batch_strided_wsquery("R", m, n, batch)
+                h.allocate_workspace()
+                rc = h.posv_batch_strided("R", "L", m, n, dA, n, n * n, dB, m, m * n, batch, None)
+                k = n
+            elif kind == "trsmptr":
+                side, trans = name.split("_")[2]
+                k = m if side == "L" else n
+                dA = _dev(torch, c["L_in"])
+                h.trsm_batch_wsquery(side, m, n, batch)
+                h.allocate_workspace()
+                rc = h.trsm_batch(side, "L", trans, "N", m, n, float(c["alpha"]), ptr_array(dA, k * k), k, ptr_array(dB, m * n), m,
+                                  batch, prec=p)
+            elif kind == "potrsptr":
+                k = n
+                dA = _dev(torch, c["L_in"])
+                h.potrs_batch_wsquery(m, n, batch)
+                h.allocate_workspace()
+                rc = h.potrs_batch("R", "L", m, n, ptr_array(dA, n * n), n, ptr_array(dB, m * n), m, batch, prec=p)
+            else:
+                assert kind == "posvptr", name
+                k = n
+                dA = _dev(torch, c["A_in"])
+                h.posv_batch_wsquery("R", m, n, batch)
+                h.allocate_workspace()
+                rc = h.posv_batch("R", "L", m, n, ptr_array(dA, n * n), n, ptr_array(dB, m * n), m, batch, None, prec=p)
+            torch.cuda.synchronize()
+            assert rc == int(c["rc"]) == 1, name
+            ref = c["B_out"]
+            assert np.abs(dB.cpu().numpy() - ref).max() <= 100 * k * eps * max(1.0, np.abs(ref).max()), name
+            if kind == "posvptr":
+                _check_potrf(c["A_in"], dA.cpu().numpy(), n, dt, Lref=c["A_out"])
+            if kind == "posvbig":
+                assert np.abs(U.pack_lower(dA.cpu().numpy(), n) - c["L_out_packed"]).max() <= 100 * n * eps * np.abs(c["A_in"]).max()
+        seen += 1
+    assert seen >= 50, seen
+
+
 # =============================================================================================
 # live A/B against the unmodified reference library on identical device buffers
 @pytest.mark.parametrize("p", ["D", "S"])

@@ -72,24 +72,31 @@ def _rows(text):
 @pytest.mark.parametrize("op", ["potrf", "trsm", "potrs", "posv"])
 @pytest.mark.parametrize("p", ["d", "s"])
 def test_reference_test_programs_run_against_our_library(op, p):
-    """the reference's own bench binaries, unmodified, on OUR library: they run to completion, and the error they
-    print against their host LAPACK loop is as small as with the reference library itself"""
+    """the reference's own bench binaries, unmodified, on OUR library: every row they print (size, GF/s, error against
+    their host LAPACK loop) is there, and the error column is as small as with the reference library itself.
+    stdout is unbuffered (stdbuf) because the programs' teardown can die inside cublasDestroy on this image -- with the
+    reference library as well (gdb: cublasDestroy_v2 <- kblasDestroy <- main) -- after all rows have been printed; the
+    exit status is therefore only required to be no worse than the reference build's."""
     if not os.path.isdir(os.path.join(BIN, "ours")):
         pytest.skip("oracle/_ref/bin not built (needs /root/reference at build time)")
+    import numpy as np
+
     args = ["-N", "32", "--batch", "200", "-c", "--nruns", "2"]
     if op in ("trsm", "potrs", "posv"):
         args += ["-SR"]
-    outs = {}
+    outs, rcs = {}, {}
     for who in ("ours", "ref"):
         for strided in ([], ["-s"]):
-            r = subprocess.run([os.path.join(BIN, who, f"test_{p}{op}_batch")] + args + strided, text=True,
+            r = subprocess.run(["stdbuf", "-o0", os.path.join(BIN, who, f"test_{p}{op}_batch")] + args + strided, text=True,
                                capture_output=True, timeout=600)
-            assert r.returncode == 0, (who, r.stdout[-2000:], r.stderr[-2000:])
             outs[(who, bool(strided))] = r.stdout
-    eps = U.EPS[{"d": __import__("numpy").float64, "s": __import__("numpy").float32}[p]]
+            rcs[(who, bool(strided))] = r.returncode
+    eps = U.EPS[{"d": np.float64, "s": np.float32}[p]]
     for strided in (False, True):
         mine, theirs = _rows(outs[("ours", strided)]), _rows(outs[("ref", strided)])
         assert mine and len(mine) == len(theirs), (outs[("ours", strided)], outs[("ref", strided)])
         for a, b in zip(mine, theirs):
             err_a, err_b = float(a[-1]), float(b[-1])       # last column: error vs the host LAPACK loop
             assert err_a == err_a and err_a <= max(100 * 32 * eps, 10 * err_b), (a, b)
+        if rcs[("ref", strided)] == 0:
+            assert rcs[("ours", strided)] == 0, outs[("ours", strided)][-500:]

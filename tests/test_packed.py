@@ -111,7 +111,7 @@ def test_pptrf_every_data_movement_variant(p, variant, n, monkeypatch):
     h = kb.Handle()
     dt = DT[p]
     sz = n * (n + 1) // 2
-    want_tag = {20: "ldg,stg", 21: "tma-in,stg", 22: "tma-in,tma-out", 23: "free"}[variant]
+    want_tag = {20: "<ldg,stg>", 21: "<tma-in,stg>", 22: "lockstep", 23: "<tma-in,tma-out>"}[variant]
     for batch in (1, 3, 4, 5, 31, 148 * 32 + 1, 40001):
         A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=batch % 97 + n)
         P0 = U.pack_lower(A0, n)

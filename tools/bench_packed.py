@@ -36,7 +36,7 @@ def timeit(fn, restore, reps=7):
 
 def main():
     kb = importlib.import_module("kblas-gpu_b200")
-    variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["20", "21", "22", "23"])]
+    variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["20", "21", "22", "23", "-1"])]
     sizes = [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["32", "24", "16", "8"])]
     batch = 1 << 20
     for prec, dt, es in (("D", torch.float64, 8), ("S", torch.float32, 4)):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""run one op once (for ncu): python tools/run_one.py potrs|trsm_LLN|posv_ptr|potrf_ptr n [batch]"""
+"""run one op twice (for ncu): python tools/run_one.py potrf|pptrf|potrs|trsm_LLN|posv_ptr|potrf_ptr n [batch]"""
 import importlib, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,6 +18,11 @@ for it in range(2):
     A = P.clone()
     if op == "potrf":
         rc = h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
+    elif op == "pptrf":
+        sz = n * (n + 1) // 2
+        PP = torch.empty((batch, sz), device="cuda", dtype=dt)
+        h.tri_pack_batch_strided("L", n, A, n, n * n, PP, sz, batch)
+        rc = h.pptrf_batch_strided("L", n, PP, sz, batch, None)
     elif op == "potrs":
         h.potrf_batch_strided("L", n, A, n, n * n, batch, None)
         rc = h.potrs_batch_strided("R", "L", m, n, A, n, n * n, B, m, m * n, batch)
