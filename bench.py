@@ -585,6 +585,8 @@ def run_configs(torch, kb, h, peak_hbm, peak_src, reps=5):
       FLOPS_POTRF = n^3/3 + n^2/2 + n/6, FLOPS_TRSM = n m^2, FLOPS_POTRS = 2 m n^2 (testing/flops.h:74-130)
     plus the packed-layout entry points (kblasx?pptrf_batch_strided).  Rank 0, N = 1 only."""
     out = []
+    # the events of _median_ms are recorded on torch's current stream: the handle must launch there too
+    h.set_stream(torch.cuda.current_stream())
     fp64_peak = measure_fp64_peak(torch)
     fp32_peak = None   # fp32 configurations here are all HBM-bound
 

@@ -89,6 +89,9 @@ int         kblasx_workspace_state(kblasHandle_t handle, int which, size_t out[4
  *  op: 0 trsm, 1 potrf, 2 potrs, 3 posv.  out[4] as above. */
 int         kblasx_wsquery_bytes(int op, int strided, char side, int m, int n, int batchCount,
                                  size_t out[4]);
+/** shared-memory slot plan of the fp64 Cholesky for 32 < n <= 256 (csrc/kernels/potrf_smem.cuh): out[I*8+K] = 8 KiB slot
+ *  of the 32 x 32 block (I, K), K <= I < nblk; returns the number of slots.  Host logic, exposed for the tests. */
+int         kblasx_potrf_smem_plan(int nblk, unsigned char out[64]);
 /** number of kernels this handle has launched since creation (the bench's gpu_launches). */
 long        kblasx_launch_count(kblasHandle_t handle);
 /** name of the kernel variant the most recent call on this handle dispatched to. */

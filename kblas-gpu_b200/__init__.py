@@ -85,6 +85,7 @@ _sig("kblas_iset_value_4", _i, _P, _i, _P, _i, _P, _i, _P, _i, _l, C.c_void_p)
 _sig("kblas_iset_value_5", _i, _P, _i, _P, _i, _P, _i, _P, _i, _P, _i, _l, C.c_void_p)
 _sig("kblasx_workspace_state", _i, _H, _i, C.POINTER(C.c_size_t))
 _sig("kblasx_wsquery_bytes", _i, _i, _i, _c, _i, _i, _i, C.POINTER(C.c_size_t))
+_sig("kblasx_potrf_smem_plan", _i, _i, C.POINTER(C.c_ubyte))
 _sig("kblasx_launch_count", _l, _H)
 _sig("kblasx_last_kernel", C.c_char_p, _H)
 _sig("kblasx_version", C.c_char_p)
@@ -164,6 +165,15 @@ def reg_size(n: int) -> bool:
 
 def closest_reg_size(n: int) -> int:
     return _lib.kblasx_closest_reg_size(n)
+
+
+def potrf_smem_plan(nblk: int):
+    """(nslots, slot[I][K]) of the shared-memory resident Cholesky (csrc/kernels/potrf_smem.cuh); host logic"""
+    out = (C.c_ubyte * 64)()
+    ns = _lib.kblasx_potrf_smem_plan(nblk, out)
+    if ns <= 0:
+        raise ValueError(error_string(ns))
+    return ns, [[out[i * 8 + k] for k in range(8)] for i in range(8)]
 
 
 WS_OPS = {"trsm": 0, "potrf": 1, "potrs": 2, "posv": 3}

@@ -6,6 +6,7 @@
 // implementations (namespace kblasx) under unmangled names.
 #include <cstring>
 #include "kblas_common.h"
+#include "kernels/potrf_smem.cuh"
 
 #define KBLASX_VERSION "kblas-b200 0.1.0 (sm_100a; potrf/trsm/potrs/posv batch; drop-in for KBLAS-GPU 3.0.0 API)"
 
@@ -120,6 +121,16 @@ int kblasx_wsquery_bytes(int op, int strided, char side, int m, int n, int batch
   }
   ws_out(s, out);
   return KBLAS_Success;
+}
+
+// shared-memory slot plan of the 32 < n <= 256 fp64 Cholesky (kernels/potrf_smem.cuh): out[I*8+K] = slot of block (I,K),
+// returns the number of 8 KiB slots (host logic, no GPU needed)
+int kblasx_potrf_smem_plan(int nblk, unsigned char out[64]) {
+  if (nblk < 1 || nblk > 8) return KBLAS_Error_WrongInput;
+  const kblasx::SmemPotrfPlan p = kblasx::plan_potrf_slots(nblk);
+  for (int i = 0; i < 8; ++i)
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = p.slot[i][k];
+  return p.nslots;
 }
 
 long kblasx_launch_count(kblasHandle_t handle) { return handle ? handle->launch_count : -1; }

@@ -8,6 +8,7 @@
 #include "kblas_common.h"
 #include "kernels/potrf_small.cuh"
 #include "kernels/potrf_panel_mma.cuh"
+#include "kernels/potrf_smem.cuh"
 #include "potrf_batch.h"
 
 namespace kblasx {
@@ -74,8 +75,32 @@ static int launch_potrf_panel_mma(KBlasHandle *h, const char *name, int n, Batch
   return KBLAS_Success;
 }
 
+// 32 < n <= 256, fp64: one CTA per matrix, factor resident in shared memory (kernels/potrf_smem.cuh)
+template <int WARPS, int MINB, bool STRIDED>
+static int launch_potrf_smem(KBlasHandle *h, const char *name, int n, BatchRef<double, STRIDED> A, int lda, int batchCount,
+                             int *info) {
+  auto kern = potrf_smem_kernel<WARPS, MINB, STRIDED>;
+  const SmemPotrfPlan plan = plan_potrf_slots((n + 31) / 32);
+  const size_t smem = PotrfSmemGeom::bytes(plan.nslots);
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)batchCount, WARPS * 32, smem, h->stream>>>(n, A, lda, batchCount, info, h->info_mode, plan);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
+  if constexpr (sizeof(T) == 8) {
+    // 30 = A/B override back to the one-warp-per-matrix kernel; 31 / 32 / 33 force 2 / 4 / 8 warps per matrix
+    const int v = h->variant_override;
+    if (n <= 256 && v != 30) {
+      const int w = v == 31 ? 2 : v == 32 ? 4 : v == 33 ? 8 : (n <= 64 ? 2 : n <= 128 ? 4 : 8);
+      if (w == 2) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2>", n, A, lda, batchCount, info);
+      if (w == 4) return launch_potrf_smem<4, 2, STRIDED>(h, "potrf_smem<W=4>", n, A, lda, batchCount, info);
+      return launch_potrf_smem<8, 1, STRIDED>(h, "potrf_smem<W=8>", n, A, lda, batchCount, info);
+    }
+  }
   // warps per matrix: few warps -> more matrices in flight per SM, which is what hides the serial
   // pivot chain of the diagonal blocks.
   // measured (B200, fp64, batch 64K, n = 64 / 128 / 256, 128-register cap): 1 warp 4.8 / 8.5 / 10.8 TFLOP/s,

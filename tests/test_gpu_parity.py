@@ -115,6 +115,61 @@ def test_potrf_strided_large_n(env, p, n):
     _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
 
 
+@pytest.mark.parametrize("variant", [-1, 30, 31, 32, 33])
+def test_dpotrf_large_n_kernel_variants(variant, monkeypatch):
+    """fp64, 32 < n <= 256: the shared-memory resident kernel (default; 31 / 32 / 33 force 2 / 4 / 8 warps per matrix)
+    and the older one-warp-per-matrix kernel (30): ragged n, padded lda, strided and pointer array, 16-byte aligned
+    and element-aligned-only matrices (the cp.async loader's two paths), LAPACK-info mode."""
+    import torch
+
+    kb = U.kblas()
+    if variant >= 0:
+        monkeypatch.setenv("KBLAS_B200_VARIANT", str(variant))
+    h = kb.Handle()
+    dt = np.float64
+    for n in (33, 40, 64, 65, 96, 100, 128, 129, 200, 224, 255, 256):
+        batch = 7
+        for lda, off in ((n, 0), (n + 3, 0), (n, 1)):
+            A0 = U.rand_spd_batch(batch, n, lda=lda, dtype=dt, seed=n + lda + off)
+            Lo = A0.copy()
+            U.oracle_potrf(Lo, n)
+            dA = _slack_copy(torch, A0, off)
+            h.potrf_batch_wsquery(n, batch)
+            h.potrf_batch_strided_wsquery(n, batch)
+            h.allocate_workspace()
+            if off == 0:
+                rc = h.potrf_batch_strided("L", n, dA, lda, n * lda, batch, None)
+            else:
+                perm = torch.randperm(batch, device="cuda")
+                rc = h.potrf_batch("L", n, _ptrs(torch, dA, off, perm, n * lda, 8), lda, batch, None, prec="D")
+            torch.cuda.synchronize()
+            assert rc == kb.KBLAS_Success
+            want = "potrf_panel_dmma" if variant == 30 else "potrf_smem" + ({31: "<W=2>", 32: "<W=4>", 33: "<W=8>"}.get(variant, ""))
+            assert want in h.last_kernel, h.last_kernel
+            got = dA[off:off + A0.size].cpu().numpy().reshape(A0.shape)
+            _check_potrf(A0, got, n, dt, Lref=Lo)
+            assert float(dA[:off].abs().sum()) == 0 and float(dA[off + A0.size:].abs().sum()) == 0
+    h.destroy()
+    # non-SPD: NaN from the bad column on (compat), LAPACK info on request
+    monkeypatch.setenv("KBLAS_B200_INFO_MODE", "lapack")
+    h = kb.Handle()
+    n, batch = 100, 5
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=77)
+    A0[1, 40, 40] = -3.0
+    A0[3, 99, 99] = -1.0
+    dA = _dev(torch, A0)
+    info = torch.full((batch,), SENT, dtype=torch.int32, device="cuda")
+    h.potrf_batch_strided_wsquery(n, batch)
+    h.allocate_workspace()
+    assert h.potrf_batch_strided("L", n, dA, n, n * n, batch, info) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert info.cpu().numpy().tolist() == [0, 41, 0, 100, 0]
+    Lo = A0.copy()
+    U.oracle_potrf(Lo, n)
+    assert np.array_equal(np.isfinite(np.tril(U.as_mats(dA.cpu().numpy(), n, n))), np.isfinite(np.tril(U.as_mats(Lo, n, n))))
+    h.destroy()
+
+
 def test_potrf_return_codes(env):
     kb, h, torch = env
     n, batch = 16, 4

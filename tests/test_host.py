@@ -181,3 +181,41 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e4
+
+
+def test_potrf_smem_slot_plan_is_a_valid_colouring(built):
+    """csrc/kernels/potrf_smem.cuh keeps the live 32 x 32 blocks of the factor in shared-memory slots assigned on the host.
+    Replay the kernel's order of events and check that no two simultaneously live blocks share a slot, and that the slot
+    count is the (nblk-J-1)(J+2) + (nblk-J-2) high-water mark (24 slots = 192 KiB for n = 256)."""
+    kb = U.kblas()
+    for nblk in range(1, 9):
+        ns, slot = kb.potrf_smem_plan(nblk)
+        live = {}
+
+        def alloc(i, k):
+            s = slot[i][k]
+            assert s < ns and s not in live.values(), (nblk, i, k, s, live)
+            live[(i, k)] = s
+
+        for i in range(nblk):
+            alloc(i, 0)
+        for i in range(1, nblk):
+            alloc(i, 1)
+        high = len(live)
+        for j in range(nblk):
+            # step a reads (j, j) and (i, j) for i > j: all must be live
+            assert all((i, j) in live for i in range(j, nblk))
+            del live[(j, j)]
+            for i in range(j + 2, nblk):
+                alloc(i, j + 2)
+            high = max(high, len(live))
+            if j + 1 < nblk:
+                # step b reads (i, k), i >= j+1, k <= j+1
+                assert all((i, k) in live for i in range(j + 1, nblk) for k in range(j + 2))
+                for k in range(j + 1):
+                    del live[(j + 1, k)]
+        assert not live
+        assert ns == high
+        want = max([(nblk - j - 1) * (j + 2) + max(0, nblk - j - 2) for j in range(nblk)] + [nblk + max(0, nblk - 1)])
+        assert ns == want, (nblk, ns, want)
+    assert kb.potrf_smem_plan(8)[0] == 24 and kb.potrf_smem_plan(4)[0] == 8 and kb.potrf_smem_plan(2)[0] == 3

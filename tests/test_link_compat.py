@@ -74,9 +74,8 @@ def _rows(text):
 def test_reference_test_programs_run_against_our_library(op, p):
     """the reference's own bench binaries, unmodified, on OUR library: every row they print (size, GF/s, error against
     their host LAPACK loop) is there, and the error column is as small as with the reference library itself.
-    stdout is unbuffered (stdbuf) because the programs' teardown can die inside cublasDestroy on this image -- with the
-    reference library as well (gdb: cublasDestroy_v2 <- kblasDestroy <- main) -- after all rows have been printed; the
-    exit status is therefore only required to be no worse than the reference build's."""
+    (The programs are built -O0 by oracle/build_ref_tests.sh: their test functions are declared int and fall off the end
+    without a return, which optimised builds turn into a crash at exit -- with the reference library as well.)"""
     if not os.path.isdir(os.path.join(BIN, "ours")):
         pytest.skip("oracle/_ref/bin not built (needs /root/reference at build time)")
     import numpy as np
@@ -98,5 +97,4 @@ def test_reference_test_programs_run_against_our_library(op, p):
         for a, b in zip(mine, theirs):
             err_a, err_b = float(a[-1]), float(b[-1])       # last column: error vs the host LAPACK loop
             assert err_a == err_a and err_a <= max(100 * 32 * eps, 10 * err_b), (a, b)
-        if rcs[("ref", strided)] == 0:
-            assert rcs[("ours", strided)] == 0, outs[("ours", strided)][-500:]
+        assert rcs[("ours", strided)] == 0 and rcs[("ref", strided)] == 0, (rcs, outs[("ours", strided)][-500:])
