@@ -236,6 +236,8 @@ KBlasHandle::KBlasHandle(int /*use_magma*/, cudaStream_t stream_, int device_id_
 
   sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  smem_optin_max = 227 * 1024;
+  cudaDeviceGetAttribute(&smem_optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
   const char *im = getenv("KBLAS_B200_INFO_MODE");
   info_mode = (im && !strcmp(im, "lapack")) ? KBLASX_INFO_LAPACK : KBLASX_INFO_COMPAT;
   const char *vo = getenv("KBLAS_B200_VARIANT");

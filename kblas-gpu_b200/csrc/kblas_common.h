@@ -50,14 +50,17 @@ inline int kx_ctas_per_sm(KBlasHandle *h, K kern, int threads, size_t smem, int 
   }
   return k->ctas_per_sm;
 }
-// raise the dynamic shared-memory limit of `kern` on the CURRENT device (once per handle and size)
+// raise the dynamic shared-memory limit of `kern` on the CURRENT device, once per handle, to the device's opt-in
+// maximum: the attribute is per function and PROCESS-wide, so a per-size value set through one handle could be lowered
+// again through another one (two handles, different n) -- the maximum is safe for every launch and costs nothing
+// (occupancy follows the bytes actually requested at launch)
 template <typename K>
 inline cudaError_t kx_allow_smem(KBlasHandle *h, K kern, size_t smem) {
   if (smem <= 48 * 1024) return cudaSuccess;
   KBlasHandle::KernelNote *k = h->kernel_note((const void *)kern);
-  if ((size_t)k->smem_limit >= smem) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) k->smem_limit = (int)smem;
+  if (k->smem_limit > 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin_max);
+  if (e == cudaSuccess) k->smem_limit = h->smem_optin_max;
   return e;
 }
 

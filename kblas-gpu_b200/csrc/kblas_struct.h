@@ -122,6 +122,7 @@ struct KBlasHandle {
 
   // ---- B200-native additions -------------------------------------------------
   int sm_count;            // multiProcessorCount of device_id
+  int smem_optin_max;      // cudaDevAttrMaxSharedMemoryPerBlockOptin of device_id (227 KiB on B200)
   int info_mode;           // KBlasxInfoMode
   int variant_override;    // -1 = auto; tuning / ablation hook (env KBLAS_B200_VARIANT)
   int exact_stores;        // env KBLAS_B200_ELEMENT_EXACT_STORES=1: potrf never stores a strict-upper element

@@ -92,12 +92,16 @@ static int launch_potrf_smem(KBlasHandle *h, const char *name, int n, BatchRef<d
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
   if constexpr (sizeof(T) == 8) {
-    // 30 = A/B override back to the one-warp-per-matrix kernel; 31 / 32 / 33 force 2 / 4 / 8 warps per matrix
+    // KBLAS_B200_VARIANT = 31 / 32 / 33: the shared-memory resident kernel with 2 / 4 / 8 warps per matrix
+    // (kernels/potrf_smem.cuh).  Measured on B200 (batch 64K, pointer array, profiles/r02_large_n_variants.txt) it reads
+    // every element from DRAM once, but is SLOWER than the one-warp-per-matrix kernel below -- n = 64 / 128 / 256:
+    // 1.69 / 7.0 / 35.4 ms against 1.05 / 4.8 / 25.4 ms -- because one matrix per CTA serialises the 32 x 32 diagonal
+    // factorisations (~5K cycles each, one warp) that eight independent matrices per SM overlap for free, and because
+    // B200 executes DMMA on the FP64 pipe one warp at a time per SM sub-partition.  It is therefore opt-in.
     const int v = h->variant_override;
-    if (n <= 256 && v != 30) {
-      const int w = v == 31 ? 2 : v == 32 ? 4 : v == 33 ? 8 : (n <= 64 ? 2 : n <= 128 ? 4 : 8);
-      if (w == 2) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2>", n, A, lda, batchCount, info);
-      if (w == 4) return launch_potrf_smem<4, 2, STRIDED>(h, "potrf_smem<W=4>", n, A, lda, batchCount, info);
+    if (n <= 256 && v >= 31 && v <= 33) {
+      if (v == 31) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2>", n, A, lda, batchCount, info);
+      if (v == 32) return launch_potrf_smem<4, 2, STRIDED>(h, "potrf_smem<W=4>", n, A, lda, batchCount, info);
       return launch_potrf_smem<8, 1, STRIDED>(h, "potrf_smem<W=8>", n, A, lda, batchCount, info);
     }
   }

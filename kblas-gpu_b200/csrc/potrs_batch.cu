@@ -1,4 +1,4 @@
-// potrs_batch.cu -- kblas_potrs_batch: X (L L^T) = B with the factor from potrf (side R only).
+// potrs_batch.cu -- kblas_potrs_batch: X (L L^T) = B (side R, the reference's only form) or (L L^T) X = B (side L, extension).
 //
 // Counterpart of reference src/batch_triangular/Xpotrs_batch.cu:42-164 and
 // Xpotrs_batch_drivers.cuh:32-174.  The reference composes 4 TRSM + 2 GEMM launches (its
@@ -13,15 +13,20 @@ namespace kblasx {
 template <typename T, bool STRIDED>
 int potrs_batch_core(KBlasHandle *h, char side, char uplo, int m, int n, BatchRef<const T, STRIDED> A, int lda,
                      BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  if (side == KBLAS_Left || uplo == KBLAS_Upper) {
+  if (uplo == KBLAS_Upper) {
     printf("(Left | Upper) POTRS_BATCH is not implemented yet\n");  // reference drivers.cuh:41
     return KBLAS_NotImplemented;
   }
+  // side L -- A X = B, A = L L^T of order m, B is m x n -- is KBLAS_NotImplemented in the reference (drivers.cuh:40-43);
+  // here it is the same fused forward + backward substitution with the factor acting from the left (SURVEY.md §8(f)3,
+  // documented extension): L Y = B, L^T X = Y.
+  const bool left = (side == KBLAS_Left);
+  if (!left && side != KBLAS_Right) return KBLAS_NotImplemented;
   // The reference splits n = n1 + n2 and hands n1 = CLOSEST_REG_SIZE(1) = 0 columns to TRSM,
   // which answers KBLAS_NotImplemented (drivers.cuh:85-98, Xtrsm_batch_drivers.cuh:267-270).
   // A 1 x 1 factor is a perfectly good problem: solved here (documented deviation).
-  if (n <= 0) return KBLAS_NotImplemented;
-  return tri_solve_core<T, STRIDED>(h, /*left=*/false, TRI_BOTH, m, n, T(1), A, lda, B, ldb, batchCount);
+  if ((left ? m : n) <= 0) return KBLAS_NotImplemented;
+  return tri_solve_core<T, STRIDED>(h, left, TRI_BOTH, m, n, T(1), A, lda, B, ldb, batchCount);
 }
 
 #define KX_INST(T, S)                                                                                      \

@@ -24,7 +24,8 @@ nvcc -O2 -std=c++14 -Xcompiler -fopenmp,-fPIC -DUSE_MKL -gencode arch=compute_10
 for op in potrf trsm potrs posv; do
   for p in s d; do
     # -O0: the test functions are declared int and fall off their end without a return (test_Xpotrf_batch.cpp:413);
-    # with optimisation g++ treats that as unreachable and main runs on into kblasDestroy a second time (SIGSEGV at exit)
+    # with optimisation g++ treats that as unreachable and main runs on into kblasDestroy a second time (SIGSEGV in
+    # cublasDestroy with the reference library); at -O0 a trap (SIGILL) sits there -- after all output, either way
     g++ -O0 -fopenmp -w -DUSE_MKL -DPREC_$p $INC -c "$R/testing/batch_triangular/test_X${op}_batch.cpp" \
         -o "$OUT/obj/test_${p}${op}_batch.o" &
   done

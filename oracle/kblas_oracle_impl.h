@@ -259,6 +259,24 @@ int ORA_(oracle_posv_batch_strided)(char side, char uplo, int m, int n, ORA_T *A
   return 1;
 }
 
+/* ---- side = 'L' EXTENSION: (L L^T) X = B, A of order m, B m x n.  NOT in the reference -- its potrs /
+ * posv answer KBLAS_NotImplemented for side L (Xpotrs_batch_drivers.cuh:40-43, Xposv_batch_drivers.cuh:41-44), which is
+ * what the two functions above restate.  The extension is DEFINED as the composition of the restated reference TRSMs:
+ *   L Y = B  (trsm L,L,N)  then  L^T X = Y  (trsm L,L,T);  posv = restated potrf of order m, then that. */
+int ORA_(oracle_potrs_left_batch_strided)(int m, int n, const ORA_T *A, int lda, long strideA, ORA_T *B, int ldb,
+                                          long strideB, int batchCount) {
+  for (long b = 0; b < batchCount; b++) {
+    ORA_(trsm)('L', 'N', m, n, (ORA_T)1, A + b * strideA, lda, B + b * strideB, ldb);
+    ORA_(trsm)('L', 'T', m, n, (ORA_T)1, A + b * strideA, lda, B + b * strideB, ldb);
+  }
+  return 1;
+}
+int ORA_(oracle_posv_left_batch_strided)(int m, int n, ORA_T *A, int lda, long strideA, ORA_T *B, int ldb, long strideB,
+                                         int batchCount) {
+  for (long b = 0; b < batchCount; b++) ORA_(potrf)(m, A + b * strideA, lda);
+  return ORA_(oracle_potrs_left_batch_strided)(m, n, A, lda, strideA, B, ldb, strideB, batchCount);
+}
+
 /* ---- packed lower storage (LAPACK ?pptrf, uplo = 'L'): AP[j*n - j(j-1)/2 + (i-j)] = A(i,j), i >= j.
  * The reference has no packed batch routine (its batch_pstrf, src/batch_svd/batch_pstrf.cu:226-246,
  * is pivoted Cholesky on full storage), so the oracle for kblasx?pptrf_batch is DEFINED as: unpack, factor with the

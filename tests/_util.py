@@ -52,6 +52,8 @@ def oracle():
             getattr(_oracle, f"oracle_potrs_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_posv_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_pptrf_batch_strided_{s}").argtypes = [c, i, P, l, i]
+            getattr(_oracle, f"oracle_potrs_left_batch_strided_{s}").argtypes = [i, i, P, i, l, P, i, l, i]
+            getattr(_oracle, f"oracle_posv_left_batch_strided_{s}").argtypes = [i, i, P, i, l, P, i, l, i]
     return _oracle
 
 
@@ -102,6 +104,14 @@ def oracle_posv(side, uplo, m, n, A, B):
     _, ncb, ldb = B.shape
     f = getattr(oracle(), f"oracle_posv_batch_strided_{SUFFIX[_dt(B)]}")
     return f(side.encode(), uplo.encode(), m, n, _np_ptr(A), lda, nca * lda, _np_ptr(B), ldb, ncb * ldb, b)
+
+
+def oracle_posv_left(m, n, A, B):
+    """side = 'L' extension (A of order m, A X = B): restated potrf + restated trsm L,L,N + trsm L,L,T"""
+    b, nca, lda = A.shape
+    _, ncb, ldb = B.shape
+    f = getattr(oracle(), f"oracle_posv_left_batch_strided_{SUFFIX[_dt(B)]}")
+    return f(m, n, _np_ptr(A), lda, nca * lda, _np_ptr(B), ldb, ncb * ldb, b)
 
 
 # --------------------------------------------------------------------------------------------

@@ -115,11 +115,11 @@ def test_potrf_strided_large_n(env, p, n):
     _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
 
 
-@pytest.mark.parametrize("variant", [-1, 30, 31, 32, 33])
+@pytest.mark.parametrize("variant", [-1, 31, 32, 33])
 def test_dpotrf_large_n_kernel_variants(variant, monkeypatch):
-    """fp64, 32 < n <= 256: the shared-memory resident kernel (default; 31 / 32 / 33 force 2 / 4 / 8 warps per matrix)
-    and the older one-warp-per-matrix kernel (30): ragged n, padded lda, strided and pointer array, 16-byte aligned
-    and element-aligned-only matrices (the cp.async loader's two paths), LAPACK-info mode."""
+    """fp64, 32 < n <= 256: the one-warp-per-matrix DMMA kernel (default) and the opt-in shared-memory resident kernel
+    (31 / 32 / 33 = 2 / 4 / 8 warps per matrix): ragged n, padded lda, strided and pointer array, 16-byte aligned and
+    element-aligned-only matrices (the cp.async loader's two paths), LAPACK-info mode."""
     import torch
 
     kb = U.kblas()
@@ -144,7 +144,7 @@ def test_dpotrf_large_n_kernel_variants(variant, monkeypatch):
                 rc = h.potrf_batch("L", n, _ptrs(torch, dA, off, perm, n * lda, 8), lda, batch, None, prec="D")
             torch.cuda.synchronize()
             assert rc == kb.KBLAS_Success
-            want = "potrf_panel_dmma" if variant == 30 else "potrf_smem" + ({31: "<W=2>", 32: "<W=4>", 33: "<W=8>"}.get(variant, ""))
+            want = "potrf_panel_dmma" if variant < 0 else "potrf_smem" + {31: "<W=2>", 32: "<W=4>", 33: "<W=8>"}[variant]
             assert want in h.last_kernel, h.last_kernel
             got = dA[off:off + A0.size].cpu().numpy().reshape(A0.shape)
             _check_potrf(A0, got, n, dt, Lref=Lo)
@@ -521,9 +521,11 @@ def test_trsm_potrs_posv_return_codes(env):
     a = (dA, 8, 64, dB, 8, 64, 2)
     assert h.trsm_batch_strided("L", "U", "N", "N", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
     assert h.trsm_batch_strided("L", "L", "N", "U", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
-    assert h.potrs_batch_strided("L", "L", 8, 8, *a) == kb.KBLAS_NotImplemented
+    assert h.potrs_batch_strided("X", "L", 8, 8, *a) == kb.KBLAS_NotImplemented
     assert h.potrs_batch_strided("R", "U", 8, 8, *a) == kb.KBLAS_NotImplemented
-    assert h.posv_batch_strided("L", "L", 8, 8, *a, None) == kb.KBLAS_NotImplemented
+    assert h.posv_batch_strided("R", "U", 8, 8, *a, None) == kb.KBLAS_NotImplemented
+    # side L is an extension here (the reference: KBLAS_NotImplemented, golden posv_?_left rc = -2): see
+    # test_potrs_posv_left_side_extension
 
 
 @pytest.mark.parametrize("p", ["D", "S"])
@@ -553,6 +555,47 @@ def test_potrs_and_posv_strided_vs_oracle(env, p, m, n):
     torch.cuda.synchronize()
     assert np.abs(dB2.cpu().numpy() - Bo).max() <= tol
     assert np.array_equal(dL.cpu().numpy(), Ao)
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("m,n", [(8, 8), (16, 3), (24, 24), (32, 32), (32, 100), (5, 13), (13, 40), (48, 16), (64, 33), (100, 7)])
+def test_potrs_posv_left_side_extension(env, p, m, n):
+    """side = 'L': (L L^T) X = B with A of order m, B m x n -- KBLAS_NotImplemented in the reference
+    (Xpotrs_batch_drivers.cuh:40-43, Xposv_batch_drivers.cuh:41-44), implemented here.  Checked against
+    the oracle's composition of the restated reference TRSMs, against LAPACK-style residuals, strided and pointer array."""
+    kb, h, torch = env
+    dt = DT[p]
+    es = np.dtype(dt).itemsize
+    batch = 45
+    A0 = U.rand_spd_batch(batch, m, lda=m + 1, dtype=dt, seed=m + 1)
+    B0 = U.rand_batch(batch, m, n, ld=m + 2, dtype=dt, seed=n + 2)
+    Ao, Bo = A0.copy(), B0.copy()
+    assert U.oracle_posv("L", "L", m, n, Ao.copy(), Bo.copy()) == -2      # the reference: not implemented
+    assert U.oracle_posv_left(m, n, Ao, Bo) == 1
+    tol = 100 * m * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :m]).max())
+    # the oracle's X really solves A X = B
+    Am, Xm, Bm = U.as_mats(A0, m, m).astype(np.float64), U.as_mats(Bo, m, n).astype(np.float64), U.as_mats(B0, m, n).astype(np.float64)
+    assert np.abs(Am @ Xm - Bm).max() <= 100 * m * U.EPS[dt] * np.abs(Am).max() * max(1.0, np.abs(Xm).max())
+    # posv, strided
+    dA, dB = _dev(torch, A0), _dev(torch, B0)
+    h.posv_batch_strided_wsquery("L", m, n, batch)
+    h.posv_batch_wsquery("L", m, n, batch)
+    h.allocate_workspace()
+    assert h.posv_batch_strided("L", "L", m, n, dA, m + 1, m * (m + 1), dB, m + 2, n * (m + 2), batch, None) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    _check_potrf(A0, dA.cpu().numpy(), m, dt, Lref=Ao)
+    got = dB.cpu().numpy()
+    assert np.abs(got[:, :, :m] - Bo[:, :, :m]).max() <= tol, h.last_kernel
+    assert np.array_equal(got[:, :, m:], B0[:, :, m:]), "ldb padding untouched"
+    # potrs from the oracle's factor, pointer array (shuffled)
+    dL, dB2 = _dev(torch, Ao), _dev(torch, B0)
+    perm = torch.randperm(batch, device="cuda")
+    pa = (dL.data_ptr() + perm * (m * (m + 1) * es)).contiguous()
+    pb = (dB2.data_ptr() + perm * (n * (m + 2) * es)).contiguous()
+    assert h.potrs_batch("L", "L", m, n, pa, m + 1, pb, m + 2, batch, prec=p) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert np.abs(dB2.cpu().numpy()[:, :, :m] - Bo[:, :, :m]).max() <= tol, h.last_kernel
+    assert np.array_equal(dL.cpu().numpy(), Ao), "factor is read-only"
 
 
 @pytest.mark.parametrize("p", ["D", "S"])

@@ -74,8 +74,10 @@ def _rows(text):
 def test_reference_test_programs_run_against_our_library(op, p):
     """the reference's own bench binaries, unmodified, on OUR library: every row they print (size, GF/s, error against
     their host LAPACK loop) is there, and the error column is as small as with the reference library itself.
-    (The programs are built -O0 by oracle/build_ref_tests.sh: their test functions are declared int and fall off the end
-    without a return, which optimised builds turn into a crash at exit -- with the reference library as well.)"""
+    Exit status: the programs' test functions are declared int and fall off their end without a return
+    (test_Xpotrf_batch.cpp:413), which is undefined behaviour -- g++ -O0 plants a trap there (SIGILL after every row has
+    been printed and the handles destroyed), optimised builds run on into a second kblasDestroy.  Both libraries get the
+    same status; stdout is unbuffered (stdbuf) so that the last row is not lost with it."""
     if not os.path.isdir(os.path.join(BIN, "ours")):
         pytest.skip("oracle/_ref/bin not built (needs /root/reference at build time)")
     import numpy as np
@@ -97,4 +99,5 @@ def test_reference_test_programs_run_against_our_library(op, p):
         for a, b in zip(mine, theirs):
             err_a, err_b = float(a[-1]), float(b[-1])       # last column: error vs the host LAPACK loop
             assert err_a == err_a and err_a <= max(100 * 32 * eps, 10 * err_b), (a, b)
-        assert rcs[("ours", strided)] == 0 and rcs[("ref", strided)] == 0, (rcs, outs[("ours", strided)][-500:])
+        # identical exit status (SIGILL from the missing return, see the docstring -- never a crash of its own)
+        assert rcs[("ours", strided)] == rcs[("ref", strided)], (rcs, outs[("ours", strided)][-500:])
