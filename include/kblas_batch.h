@@ -1,5 +1,5 @@
 /*
- * kblas_batch.h -- batched potrf / trsm / potrs / posv, uniform size.
+ * kblas_batch.h -- batched potrf / trsm / potrs / posv (+ the gemm / syrk update steps), uniform size.
  *
  * Drop-in for the hot-path subset of the reference's include/kblas_batch.h:
  *   trsm : kblas_batch.h:773-897 (C++), 948-1053 (C)   potrf: 1380-1452, 1486-1566
@@ -46,6 +46,12 @@ void kblas_potrs_batch_strided_wsquery(kblasHandle_t handle, const int m, const 
 void kblas_posv_batch_wsquery        (kblasHandle_t handle, char side, const int m, const int n, int batchCount);
 void kblas_posv_batch_strided_wsquery(kblasHandle_t handle, char side, const int m, const int n, int batchCount);
 
+void kblas_gemm_batch_strided_wsquery(kblasHandle_t handle, int batchCount);      /* reference kblas_batch.h:35 */
+void kblas_gemm_batch_nonuniform_wsquery(kblasHandle_t handle);
+void kblas_syrk_batch_wsquery(kblasHandle_t handle, const int m, int batchCount); /* reference kblas_batch.h:485 */
+void kblas_syrk_batch_nonuniform_wsquery(kblasHandle_t handle);
+void kblas_trsm_batch_nonuniform_wsquery(kblasHandle_t handle);
+
 #define KBLAS_B200_DECL_CPP(T)                                                              \
   /* op(A) X = alpha B (side L) or X op(A) = alpha B (side R); X overwrites B */            \
   int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,   \
@@ -66,6 +72,22 @@ void kblas_posv_batch_strided_wsquery(kblasHandle_t handle, char side, const int
   int kblas_potrs_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
                         const T *A, int lda, long strideA,                                  \
                         T *B, int ldb, long strideB, int batchCount);                       \
+  /* C = alpha op(A) op(B) + beta C  (reference kblas_batch.h:264-436: a cuBLAS wrapper there) */ \
+  int kblas_gemm_batch(kblasHandle_t handle, char transA, char transB, const int m,         \
+                       const int n, const int k, const T alpha, const T **A, int lda,       \
+                       const T **B, int ldb, const T beta, T **C, int ldc, int batchCount); \
+  int kblas_gemm_batch(kblasHandle_t handle, char transA, char transB, const int m,         \
+                       const int n, const int k, const T alpha, const T *A, int lda,        \
+                       long strideA, const T *B, int ldb, long strideB, const T beta,       \
+                       T *C, int ldc, long strideC, int batchCount);                        \
+  /* B(m x m, lower) = alpha op(A) op(A)^T + beta B, A m x n (trans N) or n x m (trans T)     \
+     (reference kblas_batch.h:493-755) */                                                   \
+  int kblas_syrk_batch(kblasHandle_t handle, char uplo, char trans, const int m,            \
+                       const int n, const T alpha, const T **A, int lda, const T beta,      \
+                       T **B, int ldb, int batchCount);                                     \
+  int kblas_syrk_batch(kblasHandle_t handle, char uplo, char trans, const int m,            \
+                       const int n, const T alpha, const T *A, int lda, long strideA,       \
+                       const T beta, T *B, int ldb, long strideB, int batchCount);          \
   /* potrf(A) then potrs(A, B) */                                                           \
   int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
                        T **A, int lda, T **B, int ldb, int batchCount, int *info_array);    \
@@ -102,6 +124,22 @@ extern "C" {
                            const int m, const int n,                                        \
                            const T *A, int lda, long strideA,                               \
                            T *B, int ldb, long strideB, int batchCount);                    \
+  int kblas##P##gemm_batch(kblasHandle_t handle, char transA, char transB, const int m,     \
+                           const int n, const int k, const T alpha, const T **A, int lda,   \
+                           const T **B, int ldb, const T beta, T **C, int ldc,              \
+                           int batchCount);                                                 \
+  int kblas##P##gemm_batch_strided(kblasHandle_t handle, char transA, char transB,          \
+                           const int m, const int n, const int k, const T alpha,            \
+                           const T *A, int lda, long strideA, const T *B, int ldb,          \
+                           long strideB, const T beta, T *C, int ldc, long strideC,         \
+                           int batchCount);                                                 \
+  int kblas##P##syrk_batch(kblasHandle_t handle, char uplo, char trans, const int m,        \
+                           const int n, const T alpha, const T **A, int lda, const T beta,  \
+                           T **B, int ldb, int batchCount);                                 \
+  int kblas##P##syrk_batch_strided(kblasHandle_t handle, char uplo, char trans,             \
+                           const int m, const int n, const T alpha, const T *A, int lda,    \
+                           long strideA, const T beta, T *B, int ldb, long strideB,         \
+                           int batchCount);                                                 \
   int kblas##P##posv_batch(kblasHandle_t handle, char side, char uplo,                      \
                            const int m, const int n,                                        \
                            T **A, int lda, T **B, int ldb, int batchCount, int *info_array);\

@@ -75,6 +75,8 @@ _sig("kblas_roundup", _i, _i, _i)
 for _n in ("trsm", "posv"):
     _sig(f"kblas_{_n}_batch_wsquery", None, _H, _c, _i, _i, _i)
     _sig(f"kblas_{_n}_batch_strided_wsquery", None, _H, _c, _i, _i, _i)
+_sig("kblas_gemm_batch_strided_wsquery", None, _H, _i)
+_sig("kblas_syrk_batch_wsquery", None, _H, _i, _i)
 _sig("kblas_potrf_batch_wsquery", None, _H, _i, _i)
 _sig("kblas_potrf_batch_strided_wsquery", None, _H, _i, _i)
 _sig("kblas_potrs_batch_wsquery", None, _H, _i, _i, _i)
@@ -98,6 +100,10 @@ for _p, _t in (("S", C.c_float), ("D", C.c_double)):
     _sig(f"kblasx{_p}tri_pack_batch_strided", _i, _H, _c, _i, _P, _i, _l, _P, _l, _i)
     _sig(f"kblasx{_p}tri_unpack_batch_strided", _i, _H, _c, _i, _P, _l, _P, _i, _l, _i)
     _sig(f"kblas{_p}potrf_batch", _i, _H, _c, _i, _P, _i, _i, _P)
+    _sig(f"kblas{_p}gemm_batch", _i, _H, _c, _c, _i, _i, _i, _t, _P, _i, _P, _i, _t, _P, _i, _i)
+    _sig(f"kblas{_p}gemm_batch_strided", _i, _H, _c, _c, _i, _i, _i, _t, _P, _i, _l, _P, _i, _l, _t, _P, _i, _l, _i)
+    _sig(f"kblas{_p}syrk_batch", _i, _H, _c, _c, _i, _i, _t, _P, _i, _t, _P, _i, _i)
+    _sig(f"kblas{_p}syrk_batch_strided", _i, _H, _c, _c, _i, _i, _t, _P, _i, _l, _t, _P, _i, _l, _i)
     _sig(f"kblas{_p}potrf_batch_strided", _i, _H, _c, _i, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}trsm_batch", _i, _H, _c, _c, _c, _c, _i, _i, _t, _P, _i, _P, _i, _i)
     _sig(f"kblas{_p}trsm_batch_strided", _i, _H, _c, _c, _c, _c, _i, _i, _t, _P, _i, _l, _P, _i, _l, _i)
@@ -319,6 +325,31 @@ class Handle:
         A_in's storage (padding included) with the lower triangles replaced by the factors."""
         f = getattr(_lib, f"kblasx{_prec(A_in, prec)}potrf_batch_strided_host")
         return f(self._h, _ch(uplo), n, _hptr(A_in), _hptr(A_out), lda, strideA, batch, _hptr(info))
+
+    # -- the update steps of the path as public calls (reference kblas_batch.h:264-755) ----------------
+    def gemm_batch_strided_wsquery(self, batch):
+        _lib.kblas_gemm_batch_strided_wsquery(self._h, batch)
+
+    def syrk_batch_wsquery(self, m, batch):
+        _lib.kblas_syrk_batch_wsquery(self._h, m, batch)
+
+    def gemm_batch_strided(self, transA, transB, m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, Cm, ldc, strideC, batch,
+                           prec=None):
+        f = getattr(_lib, f"kblas{_prec(Cm, prec)}gemm_batch_strided")
+        return f(self._h, _ch(transA), _ch(transB), m, n, k, alpha, _ptr(A), lda, strideA, _ptr(B), ldb, strideB, beta, _ptr(Cm), ldc,
+                 strideC, batch)
+
+    def gemm_batch(self, transA, transB, m, n, k, alpha, A_array, lda, B_array, ldb, beta, C_array, ldc, batch, prec="D"):
+        f = getattr(_lib, f"kblas{prec.upper()}gemm_batch")
+        return f(self._h, _ch(transA), _ch(transB), m, n, k, alpha, _ptr(A_array), lda, _ptr(B_array), ldb, beta, _ptr(C_array), ldc, batch)
+
+    def syrk_batch_strided(self, uplo, trans, m, n, alpha, A, lda, strideA, beta, B, ldb, strideB, batch, prec=None):
+        f = getattr(_lib, f"kblas{_prec(B, prec)}syrk_batch_strided")
+        return f(self._h, _ch(uplo), _ch(trans), m, n, alpha, _ptr(A), lda, strideA, beta, _ptr(B), ldb, strideB, batch)
+
+    def syrk_batch(self, uplo, trans, m, n, alpha, A_array, lda, beta, B_array, ldb, batch, prec="D"):
+        f = getattr(_lib, f"kblas{prec.upper()}syrk_batch")
+        return f(self._h, _ch(uplo), _ch(trans), m, n, alpha, _ptr(A_array), lda, beta, _ptr(B_array), ldb, batch)
 
     # -- compute: packed lower-triangular layout (LAPACK ?pptrf storage); no reference counterpart ------
     def pptrf_batch_strided(self, uplo, n, AP, strideAP, batch, info=None, prec=None):

@@ -54,6 +54,10 @@ void kblas_posv_batch_wsquery(kblasHandle_t h, char side, int m, int n, int batc
 void kblas_posv_batch_strided_wsquery(kblasHandle_t h, char side, int m, int n, int batchCount) {
   kblasx::posv_batch_wsquery_core(true, m, n, side, batchCount, REQ(h));
 }
+void kblas_gemm_batch_strided_wsquery(kblasHandle_t h, int batchCount) {
+  kblasx::gemm_batch_strided_wsquery_core(batchCount, REQ(h));
+}
+void kblas_syrk_batch_wsquery(kblasHandle_t h, int m, int batchCount) { kblasx::syrk_batch_wsquery_core(m, batchCount, REQ(h)); }
 #undef REQ
 
 int kblasSset_pointer_1(float **out, const float *in, int lda, long off, long batchCount, void *stream) {

@@ -277,6 +277,39 @@ int ORA_(oracle_posv_left_batch_strided)(int m, int n, ORA_T *A, int lda, long s
   return ORA_(oracle_potrs_left_batch_strided)(m, n, A, lda, strideA, B, ldb, strideB, batchCount);
 }
 
+/* kblas{S,D}gemm_batch_strided (Xgemm_batch.cu:298-363 -> cuBLAS batched GEMM, Xgemm_batch_core.cuh:549-556) and
+ * kblas{S,D}syrk_batch_strided (Xsyrk_batch.cu:137-189 -> Xsyrk_batch_strided_core, drivers.cuh:125-228; trans = 'T' reads
+ * A as n x m).  cuBLAS's accumulation order is not observable: k-sequential fma, tolerance-based parity. */
+int ORA_(oracle_gemm_batch_strided)(char transA, char transB, int m, int n, int k, ORA_T alpha, const ORA_T *A, int lda,
+                                    long strideA, const ORA_T *B, int ldb, long strideB, ORA_T beta, ORA_T *C, int ldc,
+                                    long strideC, int batchCount) {
+  if (batchCount < 1) return -10; /* KBLAS_Error_WrongInput, Xgemm_batch_core.cuh:181-182 */
+  for (long b = 0; b < batchCount; b++)
+    ORA_(gemm)(transA == 'T' || transA == 't', transB == 'T' || transB == 't', m, n, k, alpha, A + b * strideA, lda,
+               B + b * strideB, ldb, beta, C + b * strideC, ldc);
+  return 1;
+}
+int ORA_(oracle_syrk_batch_strided)(char uplo, char trans, int m, int n, ORA_T alpha, const ORA_T *A, int lda, long strideA,
+                                    ORA_T beta, ORA_T *B, int ldb, long strideB, int batchCount) {
+  if (uplo == 'U' || uplo == 'u') return -2; /* Xsyrk_batch_drivers.cuh:133-136 */
+  for (long b = 0; b < batchCount; b++) {
+    const ORA_T *Ab = A + b * strideA;
+    ORA_T *C = B + b * strideB;
+    const int ldc = ldb;
+    if (trans == 'T' || trans == 't') {
+      for (int c = 0; c < m; c++)
+        for (int r = c; r < m; r++) {
+          ORA_T s = 0;
+          for (int i = 0; i < n; i++) s = ORA_FMA(Ab[(size_t)i + (size_t)r * lda], Ab[(size_t)i + (size_t)c * lda], s);
+          C_(r, c) = ORA_FMA(alpha, s, beta * C_(r, c));
+        }
+    } else {
+      ORA_(syrk)(m, n, alpha, Ab, lda, beta, C, ldc);
+    }
+  }
+  return 1;
+}
+
 /* ---- packed lower storage (LAPACK ?pptrf, uplo = 'L'): AP[j*n - j(j-1)/2 + (i-j)] = A(i,j), i >= j.
  * The reference has no packed batch routine (its batch_pstrf, src/batch_svd/batch_pstrf.cu:226-246,
  * is pivoted Cholesky on full storage), so the oracle for kblasx?pptrf_batch is DEFINED as: unpack, factor with the

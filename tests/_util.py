@@ -52,6 +52,8 @@ def oracle():
             getattr(_oracle, f"oracle_potrs_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_posv_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_pptrf_batch_strided_{s}").argtypes = [c, i, P, l, i]
+            getattr(_oracle, f"oracle_gemm_batch_strided_{s}").argtypes = [c, c, i, i, i, t, P, i, l, P, i, l, t, P, i, l, i]
+            getattr(_oracle, f"oracle_syrk_batch_strided_{s}").argtypes = [c, c, i, i, t, P, i, l, t, P, i, l, i]
             getattr(_oracle, f"oracle_potrs_left_batch_strided_{s}").argtypes = [i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_posv_left_batch_strided_{s}").argtypes = [i, i, P, i, l, P, i, l, i]
     return _oracle
@@ -104,6 +106,23 @@ def oracle_posv(side, uplo, m, n, A, B):
     _, ncb, ldb = B.shape
     f = getattr(oracle(), f"oracle_posv_batch_strided_{SUFFIX[_dt(B)]}")
     return f(side.encode(), uplo.encode(), m, n, _np_ptr(A), lda, nca * lda, _np_ptr(B), ldb, ncb * ldb, b)
+
+
+def oracle_gemm(transA, transB, m, n, k, alpha, A, B, beta, Cm):
+    """C := alpha op(A) op(B) + beta C on (batch, ncols, ld) strided arrays"""
+    b, nca, lda = A.shape
+    _, ncb, ldb = B.shape
+    _, ncc, ldc = Cm.shape
+    f = getattr(oracle(), f"oracle_gemm_batch_strided_{SUFFIX[_dt(Cm)]}")
+    return f(transA.encode(), transB.encode(), m, n, k, alpha, _np_ptr(A), lda, nca * lda, _np_ptr(B), ldb, ncb * ldb, beta,
+             _np_ptr(Cm), ldc, ncc * ldc, b)
+
+
+def oracle_syrk(uplo, trans, m, n, alpha, A, beta, Cm):
+    b, nca, lda = A.shape
+    _, ncc, ldc = Cm.shape
+    f = getattr(oracle(), f"oracle_syrk_batch_strided_{SUFFIX[_dt(Cm)]}")
+    return f(uplo.encode(), trans.encode(), m, n, alpha, _np_ptr(A), lda, nca * lda, beta, _np_ptr(Cm), ldc, ncc * ldc, b)
 
 
 def oracle_posv_left(m, n, A, B):
