@@ -143,5 +143,11 @@ int kblasxStri_unpack_batch_strided(kblasHandle_t handle, char uplo, int n, cons
                                     float *A, int lda, long strideA, int batchCount);
 int kblasxDtri_unpack_batch_strided(kblasHandle_t handle, char uplo, int n, const double *AP, long strideAP,
                                     double *A, int lda, long strideA, int batchCount);
+/* packed matrices in HOST memory: the chunked H2D / pptrf / D2H pipeline of (4) on packed storage -- n(n+1)/2 elements per
+ * matrix cross PCIe each way instead of n*n */
+int kblasxSpptrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const float *AP_in, float *AP_out,
+                                    long strideAP, int batchCount, int *info_host);
+int kblasxDpptrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const double *AP_in, double *AP_out,
+                                    long strideAP, int batchCount, int *info_host);
 
 #endif /* KBLAS_B200_FFI_H */

@@ -95,6 +95,7 @@ _sig("kblasx_reg_size", _i, _i)
 _sig("kblasx_closest_reg_size", _i, _i)
 for _p, _t in (("S", C.c_float), ("D", C.c_double)):
     _sig(f"kblasx{_p}potrf_batch_strided_host", _i, _H, _c, _i, _P, _P, _i, _l, _i, _P)
+    _sig(f"kblasx{_p}pptrf_batch_strided_host", _i, _H, _c, _i, _P, _P, _l, _i, _P)
     _sig(f"kblasx{_p}pptrf_batch_strided", _i, _H, _c, _i, _P, _l, _i, _P)
     _sig(f"kblasx{_p}pptrf_batch", _i, _H, _c, _i, _P, _i, _P)
     _sig(f"kblasx{_p}tri_pack_batch_strided", _i, _H, _c, _i, _P, _i, _l, _P, _l, _i)
@@ -368,6 +369,11 @@ class Handle:
     def tri_unpack_batch_strided(self, uplo, n, AP, strideAP, A, lda, strideA, batch, prec=None):
         f = getattr(_lib, f"kblasx{_prec(A, prec)}tri_unpack_batch_strided")
         return f(self._h, _ch(uplo), n, _ptr(AP), strideAP, _ptr(A), lda, strideA, batch)
+
+    def pptrf_batch_strided_host(self, uplo, n, AP_in, AP_out, strideAP, batch, info=None, prec=None):
+        """packed matrices in HOST memory through the chunked H2D / pptrf / D2H pipeline (csrc/host_pipeline.cu)"""
+        f = getattr(_lib, f"kblasx{_prec(AP_in, prec)}pptrf_batch_strided_host")
+        return f(self._h, _ch(uplo), n, _hptr(AP_in), _hptr(AP_out), strideAP, batch, _hptr(info))
 
     # -- compute: pointer arrays (device arrays of device pointers) -----------------------
     def potrf_batch(self, uplo, n, A_array, lda, batch, info=None, prec="D"):

@@ -93,12 +93,13 @@ void host_pipe_destroy(void *pp) {
 // Copy `count` matrices between a host and a device array of identical (lda, stride) geometry.
 // tri: lower triangle in 8-column groups through strided 3-D copies; otherwise one contiguous copy.
 static cudaError_t copy_matrices(void *dst, const void *src, size_t es, int n, int lda, long stride, long count, bool tri,
-                                 bool last, cudaMemcpyKind kind, cudaStream_t s) {
+                                 bool last, cudaMemcpyKind kind, cudaStream_t s, long last_elems = -1) {
   // whole-array mode: count*stride elements, except that the chunk holding the batch's LAST matrix stops at that
   // matrix's last element ((count-1)*stride + lda*(n-1) + n elements): a caller with stride > lda*n owns no storage
   // behind it (the usual minimal strided allocation)
   if (!tri) {
-    const size_t elems = last ? ((size_t)(count - 1) * stride + (size_t)lda * (n - 1) + n) : (size_t)count * stride;
+    const size_t tail = last_elems >= 0 ? (size_t)last_elems : (size_t)lda * (n - 1) + n;  // elements of the last matrix
+    const size_t elems = last ? ((size_t)(count - 1) * stride + tail) : (size_t)count * stride;
     return cudaMemcpyAsync(dst, src, elems * es, kind, s);
   }
   const size_t pitch = (size_t)lda * es;
@@ -117,16 +118,20 @@ static cudaError_t copy_matrices(void *dst, const void *src, size_t es, int n, i
   return cudaSuccess;
 }
 
-template <typename T>
+// PACKED: A_in / A_out hold LAPACK packed lower matrices (n(n+1)/2 elements each, stride strideA, lda ignored) and the
+// chunks are factored by the packed kernels -- half the bytes of the full layout cross PCIe in each direction.
+template <typename T, bool PACKED>
 int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T *A_out, int lda, long strideA, int batchCount,
                              int *info_host) {
+  if (PACKED) lda = 1;  // a packed matrix is one "column" of n(n+1)/2 elements for the copy arithmetic below
+  const int nrows = PACKED ? (n * (n + 1)) / 2 : n;
   if (uplo == KBLAS_Upper) {
     printf("Upper POTRF_BATCH is not implemented yet\n");
     return KBLAS_NotImplemented;
   }
   if (batchCount <= 0) return KBLAS_UnknownError;  // same code as the device entry point's empty batch
   if (n <= 0) return KBLAS_Success;
-  if (lda < n || strideA < (long)lda * n) return KBLAS_Error_WrongInput;
+  if (PACKED ? (strideA < (long)nrows || n > 32) : (lda < n || strideA < (long)lda * n)) return PACKED && n > 32 ? KBLAS_NotImplemented : KBLAS_Error_WrongInput;
   if (!h->host_pipe) h->host_pipe = new HostPipe();
   HostPipe *p = static_cast<HostPipe *>(h->host_pipe);
   int rc = hp_init(p);
@@ -135,7 +140,7 @@ int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T 
   // transfer mode: whole-array copies unless KBLAS_B200_HOSTCOPY=tri (see the header: measured slower)
   const char *mode = getenv("KBLAS_B200_HOSTCOPY");
   const bool want_tri = mode && mode[0] == 't';
-  const bool tri = want_tri && n > 8 && (strideA % lda == 0);
+  const bool tri = !PACKED && want_tri && n > 8 && (strideA % lda == 0);
   const bool want_info = info_host && h->info_mode == KBLASX_INFO_LAPACK;
 
   // chunk: ~256 MiB of matrices per staging buffer (large enough that the per-copy latency
@@ -157,20 +162,26 @@ int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T 
     T *d = static_cast<T *>(p->dbuf[b]);
     // H2D once the previous result has left this buffer
     if (c >= HP_NBUF) check_error_ret(cudaStreamWaitEvent(p->s_in, p->ev_out[b], 0), KBLAS_CUDA_Error);
-    check_error_ret(copy_matrices(d, A_in + lo * strideA, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyHostToDevice, p->s_in),
+    check_error_ret(copy_matrices(d, A_in + lo * strideA, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyHostToDevice, p->s_in,
+                                  PACKED ? (long)nrows : -1L),
                     KBLAS_CUDA_Error);
     check_error_ret(cudaEventRecord(p->ev_in[b], p->s_in), KBLAS_CUDA_Error);
     // factorise on the handle's stream
     check_error_ret(cudaStreamWaitEvent(h->stream, p->ev_in[b], 0), KBLAS_CUDA_Error);
     {
       BatchRef<T, true> ref = {d, strideA};  // no workspace protocol here: the kernels use none
-      rc = potrf_batch_core<T, true>(h, uplo, n, ref, lda, (int)cnt, want_info ? p->dinfo[b] : nullptr);
+      if (PACKED)
+        rc = pptrf_batch_core<T, true>(h, uplo, n, ref, (int)cnt, want_info ? p->dinfo[b] : nullptr,
+                                       ((size_t)strideA * sizeof(T)) % 16 == 0);   // cudaMalloc'ed staging buffers are aligned
+      else
+        rc = potrf_batch_core<T, true>(h, uplo, n, ref, lda, (int)cnt, want_info ? p->dinfo[b] : nullptr);
     }
     if (rc != KBLAS_Success) return rc;
     check_error_ret(cudaEventRecord(p->ev_k[b], h->stream), KBLAS_CUDA_Error);
     // D2H
     check_error_ret(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0), KBLAS_CUDA_Error);
-    check_error_ret(copy_matrices(A_out + lo * strideA, d, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyDeviceToHost, p->s_out),
+    check_error_ret(copy_matrices(A_out + lo * strideA, d, sizeof(T), n, lda, strideA, cnt, tri, c + 1 == nchunks, cudaMemcpyDeviceToHost, p->s_out,
+                                  PACKED ? (long)nrows : -1L),
                     KBLAS_CUDA_Error);
     if (want_info)
       check_error_ret(cudaMemcpyAsync(info_host + lo, p->dinfo[b], (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, p->s_out),
@@ -182,18 +193,29 @@ int potrf_batch_strided_host(KBlasHandle *h, char uplo, int n, const T *A_in, T 
   return KBLAS_Success;
 }
 
-template int potrf_batch_strided_host<float>(KBlasHandle *, char, int, const float *, float *, int, long, int, int *);
-template int potrf_batch_strided_host<double>(KBlasHandle *, char, int, const double *, double *, int, long, int, int *);
+template int potrf_batch_strided_host<float, false>(KBlasHandle *, char, int, const float *, float *, int, long, int, int *);
+template int potrf_batch_strided_host<double, false>(KBlasHandle *, char, int, const double *, double *, int, long, int, int *);
+template int potrf_batch_strided_host<float, true>(KBlasHandle *, char, int, const float *, float *, int, long, int, int *);
+template int potrf_batch_strided_host<double, true>(KBlasHandle *, char, int, const double *, double *, int, long, int, int *);
 
 }  // namespace kblasx
 
 extern "C" {
 int kblasxSpotrf_batch_strided_host(KBlasHandle *handle, char uplo, int n, const float *A_in, float *A_out, int lda,
                                     long strideA, int batchCount, int *info_host) {
-  return kblasx::potrf_batch_strided_host<float>(handle, uplo, n, A_in, A_out, lda, strideA, batchCount, info_host);
+  return kblasx::potrf_batch_strided_host<float, false>(handle, uplo, n, A_in, A_out, lda, strideA, batchCount, info_host);
 }
 int kblasxDpotrf_batch_strided_host(KBlasHandle *handle, char uplo, int n, const double *A_in, double *A_out, int lda,
                                     long strideA, int batchCount, int *info_host) {
-  return kblasx::potrf_batch_strided_host<double>(handle, uplo, n, A_in, A_out, lda, strideA, batchCount, info_host);
+  return kblasx::potrf_batch_strided_host<double, false>(handle, uplo, n, A_in, A_out, lda, strideA, batchCount, info_host);
+}
+// packed lower storage in host memory (kblasx?pptrf_batch_strided semantics, same pipeline)
+int kblasxSpptrf_batch_strided_host(KBlasHandle *handle, char uplo, int n, const float *AP_in, float *AP_out, long strideAP,
+                                    int batchCount, int *info_host) {
+  return kblasx::potrf_batch_strided_host<float, true>(handle, uplo, n, AP_in, AP_out, 1, strideAP, batchCount, info_host);
+}
+int kblasxDpptrf_batch_strided_host(KBlasHandle *handle, char uplo, int n, const double *AP_in, double *AP_out, long strideAP,
+                                    int batchCount, int *info_host) {
+  return kblasx::potrf_batch_strided_host<double, true>(handle, uplo, n, AP_in, AP_out, 1, strideAP, batchCount, info_host);
 }
 }

@@ -11,6 +11,7 @@
 #include "kblas.h"
 #include "kblas_common.h"
 #include "kernels/potrf_packed.cuh"
+#include "potrf_batch.h"
 
 namespace kblasx {
 
@@ -112,6 +113,11 @@ int pptrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> AP, 
   if (n <= 24) return launch_packed_generic<T, 24, 4, 3, STRIDED>(h, "potrf_packed_generic<NP=24>", n, AP, batchCount, info);
   return launch_packed_generic<T, 32, 4, 2, STRIDED>(h, "potrf_packed_generic<NP=32>", n, AP, batchCount, info);
 }
+
+template int pptrf_batch_core<float, true>(KBlasHandle *, char, int, BatchRef<float, true>, int, int *, bool);
+template int pptrf_batch_core<double, true>(KBlasHandle *, char, int, BatchRef<double, true>, int, int *, bool);
+template int pptrf_batch_core<float, false>(KBlasHandle *, char, int, BatchRef<float, false>, int, int *, bool);
+template int pptrf_batch_core<double, false>(KBlasHandle *, char, int, BatchRef<double, false>, int, int *, bool);
 
 template <typename T, bool STRIDED, bool UNPACK>
 static int tri_pack(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, int lda, BatchRef<T, STRIDED> AP, int batchCount) {

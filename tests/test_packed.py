@@ -228,3 +228,32 @@ def test_full_size_pptrf_properties(env, p, n):
         Am = A0[sl].transpose(1, 2).double()
         R = Am - Lm @ Lm.transpose(1, 2)
         assert (R.flatten(1).norm(dim=1) / Am.flatten(1).norm(dim=1)).max().item() <= 10 * n * eps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("n,pad", [(32, 0), (8, 0), (20, 3), (16, 2)])
+def test_pptrf_host_pipeline(env, p, n, pad, monkeypatch):
+    """kblasx?pptrf_batch_strided_host: packed matrices in host memory through the chunked 3-stream pipeline ==
+    H2D + kblasx?pptrf_batch_strided + D2H, bit for bit, in place and out of place; the last chunk stops at the last
+    element of the last matrix (minimal strided allocation)."""
+    kb, h, torch = env
+    dt = DT[p]
+    batch = 301
+    sz = n * (n + 1) // 2
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n + 5)
+    P0 = np.full((batch, sz + pad), -7.25, dtype=dt)
+    P0[:, :sz] = U.pack_lower(A0, n)
+    dP = torch.from_numpy(P0).cuda()
+    assert h.pptrf_batch_strided("L", n, dP, sz + pad, batch, None) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    want = dP.cpu().numpy()
+    monkeypatch.setenv("KBLAS_B200_HOSTCHUNK_MB", str(6.5 * (sz + pad) * np.dtype(dt).itemsize / (1 << 20)))
+    flat = P0.flatten()[: (batch - 1) * (sz + pad) + sz].copy()     # minimal allocation: nothing behind the last matrix
+    assert h.pptrf_batch_strided_host("L", n, flat, flat, sz + pad, batch) == kb.KBLAS_Success
+    assert np.array_equal(flat, want.flatten()[: flat.size])
+    src, out = P0.copy(), np.full_like(P0, 9.5)
+    assert h.pptrf_batch_strided_host("L", n, src, out, sz + pad, batch) == kb.KBLAS_Success
+    assert np.array_equal(src, P0), "AP_in is read-only"
+    assert np.array_equal(out[:, :sz], want[:, :sz])
+    assert h.pptrf_batch_strided_host("U", n, src, out, sz + pad, batch) == kb.KBLAS_NotImplemented
