@@ -544,10 +544,11 @@ def main():
             "metric": "dpotrf_batch_strided n=32 fp64 throughput",
             "value": value, "unit": "matrices/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if args.batch else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"strided dpotrf_batch n=32 lda=32 batch={total_batch} fp64 "
-                                   f"({'BASELINE configs[1] at n=32' if world == 1 else 'BASELINE configs[4] layout: 2^20 matrices per GPU, contiguous slabs'})",
+                                   + (f"(BASELINE configs[4]: fixed batch of {total_batch} matrices split by contiguous slab over {world} GPU(s))" if args.batch
+                                      else ('(BASELINE configs[1] at n=32)' if world == 1 else '(BASELINE configs[4] layout: 2^20 matrices per GPU, contiguous slabs)')),
                        "batch_total": total_batch, "batch_per_gpu": batch, "n": n, "uplo": "L",
                        "l2_policy": f"inputs larger than L2: {bytes_batch / 2**30:.1f} GiB per step per GPU, a fresh buffer every step",
                        "parallelism": f"batch slab x{world}, no collective"},
