@@ -211,6 +211,32 @@ def test_potrf_non_spd_matches_reference_behaviour(env, p):
     assert (info.cpu().numpy() == SENT).all()
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+def test_potrf_element_exact_stores_opt_out(p, monkeypatch):
+    """KBLAS_B200_ELEMENT_EXACT_STORES=1 (read at kblasCreate): the n % 8 == 0 fast path, which re-writes the strict-upper
+    elements sharing a sector with the diagonal with their own bits, is replaced by the element-exact kernel (ADVICE round 1:
+    opt-out for callers that update the upper triangle concurrently).  Same factor, bit for bit."""
+    import torch
+
+    kb = U.kblas()
+    dt = DT[p]
+    n, batch = 32, 777
+    A0 = U.rand_spd_batch(batch, n, dtype=dt, seed=21)
+    h0 = kb.Handle()
+    d0 = _dev(torch, A0)
+    assert h0.potrf_batch_strided("L", n, d0, n, n * n, batch, None) == kb.KBLAS_Success
+    assert "EX=true" in h0.last_kernel
+    monkeypatch.setenv("KBLAS_B200_ELEMENT_EXACT_STORES", "1")
+    h1 = kb.Handle()
+    d1 = _dev(torch, A0)
+    assert h1.potrf_batch_strided("L", n, d1, n, n * n, batch, None) == kb.KBLAS_Success
+    assert "EX=false" in h1.last_kernel
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d1)
+    h0.destroy()
+    h1.destroy()
+
+
 def test_potrf_lapack_info_mode_is_opt_in(env):
     kb, _, torch = env
     os.environ["KBLAS_B200_INFO_MODE"] = "lapack"
