@@ -12,12 +12,16 @@
 //   * 32 x 32 blocks are stored column-major with the row index XOR-swizzled by 4*(col % 4): the DMMA m8n8k4 fragment
 //     loads (8 rows x 4 columns per instruction), the row-per-lane accesses of the substitution and the 16-byte cp.async
 //     writes are all bank-conflict free without padding.
-//   * update  P[I] -= sum_K L[I][K] L[J][K]^T  on FP64 DMMA (mma.sync m8n8k4), operands from shared memory, two
-//     interleaved accumulator sets per tile (the dependent-DMMA latency is ~150 cycles on B200:
-//     profiles/r01_microbench_pipes.txt) -- 16 independent accumulators per warp, 16-row x 32-column work units;
-//   * look-ahead: the two units of the NEXT diagonal block go to warps 0/1 first, warp 0 then factors it (row per lane,
-//     shuffle pivot, shared-memory column broadcast) while the other warps update the rest of the panel; the rows
-//     below are solved against it (row per lane) and leave for global memory as whole 256-byte column segments.
+//   * update  P[I] -= sum_K L[I][K] L[J][K]^T  on FP64 DMMA (mma.sync m8n8k4), operands from shared memory, in 8-row x
+//     32-column strips with two K-interleaved accumulator sets (the dependent-DMMA latency is ~150 cycles on B200 and a
+//     sub-partition runs one warp's DMMAs at a time: profiles/r01_microbench_pipes.txt).  Strips of the off-diagonal
+//     blocks are handed out through a shared counter, so the late panels (one or two row blocks, long inner dimension)
+//     still occupy every warp -- the first version, with whole 16-row units assigned statically, spent 48 % of its stall
+//     samples in the CTA barrier (profiles/r02_ncu_dpotrf256_smem_potrf_smem_W8.json);
+//   * look-ahead: the four strips of the NEXT diagonal block go to warps 0..3 first, warp 0 then factors it (row per lane;
+//     the next column's pivot is formed in registers and its rsqrt overlaps the current column's shared-memory broadcast)
+//     while the other warps update the rest of the panel; the rows below are solved against it (row per lane) and leave
+//     for global memory as whole 256-byte column segments.
 // Replaces the reference's recursion for these sizes: 14 / 41 / 108 launches with every tile making 5-8 global round trips
 // (Xpotrf_batch_drivers.cuh:94-133, Xsyrk_batch_drivers.cuh:234-323).
 #pragma once
@@ -65,7 +69,7 @@ inline SmemPotrfPlan plan_potrf_slots(int nblk) {
 struct PotrfSmemGeom {
   static constexpr int NB = 32;
   static constexpr int BLK = NB * NB;  // doubles per slot
-  static size_t bytes(int nslots) { return (size_t)nslots * BLK * sizeof(double) + NB * sizeof(double) + 64 + 64; }  // blocks, 1/diag, slot table
+  static size_t bytes(int nslots) { return (size_t)nslots * BLK * sizeof(double) + NB * sizeof(double) + 64 + 64; }  // blocks, 1/diag, slot table, strip counter
 };
 
 // element (r, c) of a swizzled 32 x 32 block
@@ -139,18 +143,22 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
   };
 
   // ---- F(J): factor the diagonal block in place (one warp, lane = row), store its lower triangle -------------------
+  // The pivot of column j+1 is formed from registers alone -- lane j+1 holds L[j+1][j] (its own p[j]) and p[j+1] -- and
+  // broadcast BEFORE column j goes through shared memory, so the shuffle -> rsqrt (62 cycles) chain of the next column
+  // overlaps the trailing update of this one instead of queueing behind its STS / LDS round trip.
   auto factor_diag = [&](int J) {
     double *D = blk(J, J);
     const int jb = (n - NB * J < NB) ? (n - NB * J) : NB;
     double p[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) p[c] = D[sw_idx(lane, c)];
+    double dcur = __shfl_sync(0xffffffffu, p[0], 0);
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      const double d = __shfl_sync(0xffffffffu, p[j], j);
-      if (info_mode && bad == 0 && j < jb && !(d > 0.0)) bad = NB * J + j + 1;
-      const double r = rsqrt(d);
+      if (info_mode && bad == 0 && j < jb && !(dcur > 0.0)) bad = NB * J + j + 1;
+      const double r = rsqrt(dcur);
       p[j] *= r;
+      if (j + 1 < NB) dcur = __shfl_sync(0xffffffffu, fma(-p[j], p[j], p[j + 1]), j + 1);
       D[sw_idx(lane, j)] = p[j];
       if (lane == j) invd[j] = r;
       __syncwarp();
@@ -195,45 +203,55 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
     for (int c = 0; c < NB; ++c) stg_stream_if(g + (long)c * lda, p[c], row < n && c < jb);
   };
 
-  // ---- U unit: rows 16h .. 16h+15 of block (I, Jn) -= sum_{K < Jn} L[I][K] L[Jn][K]^T on DMMA ---------------------
-  auto update_unit = [&](int I, int h, int Jn) {
+  // ---- U strip: rows 8q .. 8q+7 of block (I, Jn) -= sum_{K < Jn} L[I][K] L[Jn][K]^T on DMMA.  8-row strips (4 per block)
+  // keep all warps busy in the late panels, where only one or two row blocks are left but the inner dimension is long;
+  // two K-interleaved accumulator sets x 4 column tiles = 8 independent DMMA chains per warp.
+  auto update_strip = [&](int I, int q, int Jn) {
     const int fr = lane >> 2, fk = lane & 3, sw = fk << 2;
-    double acc[2][2][4][2];
+    double acc[2][4][2];
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-      for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) acc[s][rb][cb][0] = acc[s][rb][cb][1] = 0.0;
+      for (int cb = 0; cb < 4; ++cb) acc[s2][cb][0] = acc[s2][cb][1] = 0.0;
+    const int arow = (8 * q + fr) ^ sw;
     for (int K = 0; K < Jn; ++K) {
-      const double *a_blk = blk(I, K) + fk * 32;
+      const double *a_blk = blk(I, K) + fk * 32 + arow;
       const double *b_blk = blk(Jn, K) + fk * 32;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        double af[2], bf[4];
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) af[rb] = a_blk[ks * 128 + ((16 * h + 8 * rb + fr) ^ sw)];
+        double bf[4];
+        const double af = a_blk[ks * 128];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) bf[cb] = b_blk[ks * 128 + ((8 * cb + fr) ^ sw)];
 #pragma unroll
-        for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb) dmma_m8n8k4(acc[ks & 1][rb][cb][0], acc[ks & 1][rb][cb][1], af[rb], bf[cb]);
+        for (int cb = 0; cb < 4; ++cb) dmma_m8n8k4(acc[ks & 1][cb][0], acc[ks & 1][cb][1], af, bf[cb]);
       }
     }
     double *P = blk(I, Jn);
 #pragma unroll
-    for (int rb = 0; rb < 2; ++rb)
+    for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-      for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int r = 16 * h + 8 * rb + fr, c = 8 * cb + 2 * fk + e;
-          P[sw_idx(r, c)] -= acc[0][rb][cb][e] + acc[1][rb][cb][e];
-        }
+      for (int e = 0; e < 2; ++e) {
+        const int r = 8 * q + fr, c = 8 * cb + 2 * fk + e;
+        P[sw_idx(r, c)] -= acc[0][cb][e] + acc[1][cb][e];
+      }
+  };
+
+  // off-diagonal strips of panel Jn, handed out through a shared counter (whoever is free takes the next one)
+  int *const strip_ctr = reinterpret_cast<int *>(slot_tab + 64);
+  auto offdiag_strips = [&](int Jn) {
+    const int nstrips = 4 * (nblk - Jn - 1);
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(strip_ctr, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= nstrips) break;
+      update_strip(Jn + 1 + (u >> 2), u & 3, Jn);
+    }
   };
 
   // ================================================================================================================
+  constexpr int DW = WARPS < 4 ? WARPS : 4;  // warps that share the 4 strips of the next diagonal block
   load_panel(0);
   load_panel(1);
   cp_async_wait<1>();  // panel 0 has landed (this thread's copies) ...
@@ -244,8 +262,9 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
   __syncthreads();
 
   for (int J = 0; J < nblk; ++J) {
-    // ---- step a: rows below the diagonal block of panel J --------------------------------------------------------
+    // ---- S: rows below the diagonal block of panel J ---------------------------------------------------------------
     for (int I = J + 1 + warp; I < nblk; I += WARPS) solve_block(I, J);
+    if (tid == 0) *strip_ctr = 0;
     __syncthreads();
     if (J + 1 >= nblk) break;
     // ---- look-ahead load of panel J+2 (its slots are free now), panel J+1 must have landed ----------------------
@@ -254,25 +273,17 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
     __syncthreads();
     pad_diag(J + 1);
     __syncthreads();
-    // ---- step b: panel J+1 -= L[.][0..J] L[J+1][0..J]^T; warps 0/1 own the diagonal block, warp 0 then factors it ----
+    // ---- U + F: panel J+1 -= L[.][0..J] L[J+1][0..J]^T.  The first DW warps take the 4 strips of the next diagonal block,
+    //      warp 0 then factors it WHILE everybody else works through the off-diagonal strips -----------------------------
     const int Jn = J + 1;
-    const int units = 2 * (nblk - Jn);
-    if (WARPS == 1) {
-      for (int u = 0; u < units; ++u) update_unit(Jn + (u >> 1), u & 1, Jn);
-      __syncwarp();
-      factor_diag(Jn);
+    if (warp < DW) {
+      for (int q = warp; q < 4; q += DW) update_strip(Jn, q, Jn);
+      if (DW > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * DW) : "memory");
+      else __syncwarp();
+      if (warp == 0) factor_diag(Jn);
+      else offdiag_strips(Jn);
     } else {
-      if (warp == 0) {
-        update_unit(Jn, 0, Jn);
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        factor_diag(Jn);
-      } else {
-        if (warp == 1) {
-          update_unit(Jn, 1, Jn);
-          asm volatile("bar.sync 1, 64;" ::: "memory");
-        }
-        for (int u = 2 + (warp - 1); u < units; u += WARPS - 1) update_unit(Jn + (u >> 1), u & 1, Jn);
-      }
+      offdiag_strips(Jn);
     }
     __syncthreads();
   }

@@ -99,9 +99,11 @@ static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
     // factorisations (~5K cycles each, one warp) that eight independent matrices per SM overlap for free, and because
     // B200 executes DMMA on the FP64 pipe one warp at a time per SM sub-partition.  It is therefore opt-in.
     const int v = h->variant_override;
-    if (n <= 256 && v >= 31 && v <= 33) {
-      if (v == 31) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2>", n, A, lda, batchCount, info);
-      if (v == 32) return launch_potrf_smem<4, 2, STRIDED>(h, "potrf_smem<W=4>", n, A, lda, batchCount, info);
+    if (n <= 256 && v >= 31 && v <= 35) {
+      if (v == 31) return launch_potrf_smem<2, 8, STRIDED>(h, "potrf_smem<W=2,MB=8>", n, A, lda, batchCount, info);
+      if (v == 34) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2,MB=4>", n, A, lda, batchCount, info);
+      if (v == 32) return launch_potrf_smem<4, 4, STRIDED>(h, "potrf_smem<W=4,MB=4>", n, A, lda, batchCount, info);
+      if (v == 35) return launch_potrf_smem<4, 2, STRIDED>(h, "potrf_smem<W=4,MB=2>", n, A, lda, batchCount, info);
       return launch_potrf_smem<8, 1, STRIDED>(h, "potrf_smem<W=8>", n, A, lda, batchCount, info);
     }
   }
