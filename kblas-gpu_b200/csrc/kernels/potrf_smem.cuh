@@ -87,10 +87,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// KX_SMEM_TRACE (tools/trace_smem.cu only): thread 0 / lane 0 of warps 0 and 1 record clock64() at every phase boundary
+#ifdef KX_SMEM_TRACE
+#define KX_TRACE_PARAM , long long *__restrict__ trace
+#define KX_T(slot_)                                                                     \
+  do {                                                                                  \
+    if (lane == 0 && warp < 2 && blockIdx.x < 4) trace[(blockIdx.x * 2 + warp) * 128 + (slot_)] = clock64(); \
+  } while (0)
+#else
+#define KX_TRACE_PARAM
+#define KX_T(slot_) do { } while (0)
+#endif
+
 template <int WARPS, int MINB, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
-                  const int info_mode, const SmemPotrfPlan plan) {
+                  const int info_mode, const SmemPotrfPlan plan KX_TRACE_PARAM) {
   constexpr int NB = 32, BLK = NB * NB, THREADS = WARPS * 32;
   extern __shared__ __align__(128) unsigned char smem_ps[];
   double *const blocks = reinterpret_cast<double *>(smem_ps);
@@ -252,20 +264,26 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
 
   // ================================================================================================================
   constexpr int DW = WARPS < 4 ? WARPS : 4;  // warps that share the 4 strips of the next diagonal block
+  KX_T(0);
   load_panel(0);
   load_panel(1);
   cp_async_wait<1>();  // panel 0 has landed (this thread's copies) ...
   __syncthreads();     // ... and everybody's
+  KX_T(1);
   pad_diag(0);
   __syncthreads();
   if (warp == 0) factor_diag(0);
+  KX_T(2);
   __syncthreads();
+  KX_T(3);
 
   for (int J = 0; J < nblk; ++J) {
     // ---- S: rows below the diagonal block of panel J ---------------------------------------------------------------
     for (int I = J + 1 + warp; I < nblk; I += WARPS) solve_block(I, J);
+    KX_T(8 + 8 * J + 0);  // own S blocks done
     if (tid == 0) *strip_ctr = 0;
     __syncthreads();
+    KX_T(8 + 8 * J + 1);  // S phase over
     if (J + 1 >= nblk) break;
     // ---- look-ahead load of panel J+2 (its slots are free now), panel J+1 must have landed ----------------------
     load_panel(J + 2);
@@ -273,19 +291,24 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
     __syncthreads();
     pad_diag(J + 1);
     __syncthreads();
+    KX_T(8 + 8 * J + 2);  // next panel resident
     // ---- U + F: panel J+1 -= L[.][0..J] L[J+1][0..J]^T.  The first DW warps take the 4 strips of the next diagonal block,
     //      warp 0 then factors it WHILE everybody else works through the off-diagonal strips -----------------------------
     const int Jn = J + 1;
     if (warp < DW) {
       for (int q = warp; q < 4; q += DW) update_strip(Jn, q, Jn);
+      KX_T(8 + 8 * J + 3);  // own diagonal strip done
       if (DW > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * DW) : "memory");
       else __syncwarp();
+      KX_T(8 + 8 * J + 4);  // diagonal block updated
       if (warp == 0) factor_diag(Jn);
       else offdiag_strips(Jn);
     } else {
       offdiag_strips(Jn);
     }
+    KX_T(8 + 8 * J + 5);  // F (warp 0) / off-diagonal strips (warp 1) done
     __syncthreads();
+    KX_T(8 + 8 * J + 6);
   }
   cp_async_wait<0>();
   if (info_mode && tid == 0) info[blockIdx.x] = bad;

@@ -92,12 +92,12 @@ static int launch_potrf_smem(KBlasHandle *h, const char *name, int n, BatchRef<d
 template <typename T, bool STRIDED>
 static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
   if constexpr (sizeof(T) == 8) {
-    // KBLAS_B200_VARIANT = 31 / 32 / 33: the shared-memory resident kernel with 2 / 4 / 8 warps per matrix
+    // KBLAS_B200_VARIANT = 31 / 34 (2 warps), 32 / 35 (4 warps), 33 (8 warps per matrix): the shared-memory resident kernel
     // (kernels/potrf_smem.cuh).  Measured on B200 (batch 64K, pointer array, profiles/r02_large_n_variants.txt) it reads
-    // every element from DRAM once, but is SLOWER than the one-warp-per-matrix kernel below -- n = 64 / 128 / 256:
-    // 1.69 / 7.0 / 35.4 ms against 1.05 / 4.8 / 25.4 ms -- because one matrix per CTA serialises the 32 x 32 diagonal
-    // factorisations (~5K cycles each, one warp) that eight independent matrices per SM overlap for free, and because
-    // B200 executes DMMA on the FP64 pipe one warp at a time per SM sub-partition.  It is therefore opt-in.
+    // every element from DRAM once (1.1x compulsory against 4.6x), but is SLOWER than the one-warp-per-matrix kernel below
+    // -- n = 64 / 128 / 256: 1.48 / 5.24 / 31.4 ms against 1.05 / 4.80 / 25.5 ms -- because one matrix per CTA has nothing to
+    // overlap the 32-step dependent chains of the diagonal factorisation (7-10K cycles) and of the row solves (4-6K cycles
+    // per block) with (profiles/r02_smem_phase_trace.txt), which eight independent matrices per SM overlap for free.  Opt-in.
     const int v = h->variant_override;
     if (n <= 256 && v >= 31 && v <= 35) {
       if (v == 31) return launch_potrf_smem<2, 8, STRIDED>(h, "potrf_smem<W=2,MB=8>", n, A, lda, batchCount, info);
