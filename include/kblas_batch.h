@@ -52,6 +52,16 @@ void kblas_syrk_batch_wsquery(kblasHandle_t handle, const int m, int batchCount)
 void kblas_syrk_batch_nonuniform_wsquery(kblasHandle_t handle);
 void kblas_trsm_batch_nonuniform_wsquery(kblasHandle_t handle);
 
+/* the consumers of the factor (reference kblas_batch.h:1611-1622, 1840-1851, 2321-2332, 2547-2558) */
+void kblas_trtri_batch_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_trtri_batch_strided_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_lauum_batch_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_lauum_batch_strided_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_potri_batch_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_potri_batch_strided_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_poti_batch_wsquery(kblasHandle_t handle, const int n, int batchCount);
+void kblas_poti_batch_strided_wsquery(kblasHandle_t handle, const int n, int batchCount);
+
 #define KBLAS_B200_DECL_CPP(T)                                                              \
   /* op(A) X = alpha B (side L) or X op(A) = alpha B (side R); X overwrites B */            \
   int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag,   \
@@ -88,6 +98,16 @@ void kblas_trsm_batch_nonuniform_wsquery(kblasHandle_t handle);
   int kblas_syrk_batch(kblasHandle_t handle, char uplo, char trans, const int m,            \
                        const int n, const T alpha, const T *A, int lda, long strideA,       \
                        const T beta, T *B, int ldb, long strideB, int batchCount);          \
+  /* in place on the lower triangle: A := A^-1 (trtri), A := A^T A (lauum), A(=L) := (L L^T)^-1 (potri),   \
+     A := A^-1 for SPD A (poti = potrf + potri); reference kblas_batch.h:1627-1797, 1856-2032, 2337-2506, 2563-2729 */ \
+  int kblas_trtri_batch(kblasHandle_t handle, char uplo, char diag, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas_trtri_batch(kblasHandle_t handle, char uplo, char diag, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas_lauum_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas_lauum_batch(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas_potri_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas_potri_batch(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas_poti_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas_poti_batch(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
   /* potrf(A) then potrs(A, B) */                                                           \
   int kblas_posv_batch(kblasHandle_t handle, char side, char uplo, const int m, const int n,\
                        T **A, int lda, T **B, int ldb, int batchCount, int *info_array);    \
@@ -140,6 +160,14 @@ extern "C" {
                            const int m, const int n, const T alpha, const T *A, int lda,    \
                            long strideA, const T beta, T *B, int ldb, long strideB,         \
                            int batchCount);                                                 \
+  int kblas##P##trtri_batch(kblasHandle_t handle, char uplo, char diag, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas##P##trtri_batch_strided(kblasHandle_t handle, char uplo, char diag, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas##P##lauum_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas##P##lauum_batch_strided(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas##P##potri_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas##P##potri_batch_strided(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
+  int kblas##P##poti_batch(kblasHandle_t handle, char uplo, const int n, T **A, int lda, int batchCount, int *info_array); \
+  int kblas##P##poti_batch_strided(kblasHandle_t handle, char uplo, const int n, T *A, int lda, long strideA, int batchCount, int *info_array); \
   int kblas##P##posv_batch(kblasHandle_t handle, char side, char uplo,                      \
                            const int m, const int n,                                        \
                            T **A, int lda, T **B, int ldb, int batchCount, int *info_array);\

@@ -53,6 +53,14 @@ void kblas_posv_batch_wsquery(kblasHandle_t handle, char side, int m, int n, int
 void kblas_posv_batch_strided_wsquery(kblasHandle_t handle, char side, int m, int n, int batchCount);
 void kblas_gemm_batch_strided_wsquery(kblasHandle_t handle, int batchCount);       /* workspace_queries.cu:216-219 */
 void kblas_syrk_batch_wsquery(kblasHandle_t handle, int m, int batchCount);        /* workspace_queries.cu:239-242 */
+void kblas_trtri_batch_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_trtri_batch_strided_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_lauum_batch_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_lauum_batch_strided_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_potri_batch_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_potri_batch_strided_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_poti_batch_wsquery(kblasHandle_t handle, int n, int batchCount);
+void kblas_poti_batch_strided_wsquery(kblasHandle_t handle, int n, int batchCount);
 
 /* (2) pointer-array / value helpers the reference's own test binaries call
  *     (src/Xhelper_funcs.ch:48-55 -> S/D suffix replaces the C++ overload;

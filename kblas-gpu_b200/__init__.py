@@ -77,6 +77,9 @@ for _n in ("trsm", "posv"):
     _sig(f"kblas_{_n}_batch_strided_wsquery", None, _H, _c, _i, _i, _i)
 _sig("kblas_gemm_batch_strided_wsquery", None, _H, _i)
 _sig("kblas_syrk_batch_wsquery", None, _H, _i, _i)
+for _n in ("trtri", "lauum", "potri", "poti"):
+    _sig(f"kblas_{_n}_batch_wsquery", None, _H, _i, _i)
+    _sig(f"kblas_{_n}_batch_strided_wsquery", None, _H, _i, _i)
 _sig("kblas_potrf_batch_wsquery", None, _H, _i, _i)
 _sig("kblas_potrf_batch_strided_wsquery", None, _H, _i, _i)
 _sig("kblas_potrs_batch_wsquery", None, _H, _i, _i, _i)
@@ -101,6 +104,11 @@ for _p, _t in (("S", C.c_float), ("D", C.c_double)):
     _sig(f"kblasx{_p}tri_pack_batch_strided", _i, _H, _c, _i, _P, _i, _l, _P, _l, _i)
     _sig(f"kblasx{_p}tri_unpack_batch_strided", _i, _H, _c, _i, _P, _l, _P, _i, _l, _i)
     _sig(f"kblas{_p}potrf_batch", _i, _H, _c, _i, _P, _i, _i, _P)
+    _sig(f"kblas{_p}trtri_batch", _i, _H, _c, _c, _i, _P, _i, _i, _P)
+    _sig(f"kblas{_p}trtri_batch_strided", _i, _H, _c, _c, _i, _P, _i, _l, _i, _P)
+    for _n in ("lauum", "potri", "poti"):
+        _sig(f"kblas{_p}{_n}_batch", _i, _H, _c, _i, _P, _i, _i, _P)
+        _sig(f"kblas{_p}{_n}_batch_strided", _i, _H, _c, _i, _P, _i, _l, _i, _P)
     _sig(f"kblas{_p}gemm_batch", _i, _H, _c, _c, _i, _i, _i, _t, _P, _i, _P, _i, _t, _P, _i, _i)
     _sig(f"kblas{_p}gemm_batch_strided", _i, _H, _c, _c, _i, _i, _i, _t, _P, _i, _l, _P, _i, _l, _t, _P, _i, _l, _i)
     _sig(f"kblas{_p}syrk_batch", _i, _H, _c, _c, _i, _i, _t, _P, _i, _t, _P, _i, _i)
@@ -351,6 +359,23 @@ class Handle:
     def syrk_batch(self, uplo, trans, m, n, alpha, A_array, lda, beta, B_array, ldb, batch, prec="D"):
         f = getattr(_lib, f"kblas{prec.upper()}syrk_batch")
         return f(self._h, _ch(uplo), _ch(trans), m, n, alpha, _ptr(A_array), lda, beta, _ptr(B_array), ldb, batch)
+
+    # -- the consumers of the factor (reference kblas_batch.h:1611-2729): in place on the lower triangle -----------
+    def inv_batch_wsquery(self, which, n, batch, strided=True):
+        getattr(_lib, f"kblas_{which}_batch{'_strided' if strided else ''}_wsquery")(self._h, n, batch)
+
+    def inv_batch_strided(self, which, uplo, n, A, lda, strideA, batch, info=None, diag="N", prec=None):
+        """which = 'trtri' (A := A^-1), 'lauum' (A := A^T A), 'potri' (A = L := (L L^T)^-1), 'poti' (SPD A := A^-1)"""
+        f = getattr(_lib, f"kblas{_prec(A, prec)}{which}_batch_strided")
+        if which == "trtri":
+            return f(self._h, _ch(uplo), _ch(diag), n, _ptr(A), lda, strideA, batch, _ptr(info))
+        return f(self._h, _ch(uplo), n, _ptr(A), lda, strideA, batch, _ptr(info))
+
+    def inv_batch(self, which, uplo, n, A_array, lda, batch, info=None, diag="N", prec="D"):
+        f = getattr(_lib, f"kblas{prec.upper()}{which}_batch")
+        if which == "trtri":
+            return f(self._h, _ch(uplo), _ch(diag), n, _ptr(A_array), lda, batch, _ptr(info))
+        return f(self._h, _ch(uplo), n, _ptr(A_array), lda, batch, _ptr(info))
 
     # -- compute: packed lower-triangular layout (LAPACK ?pptrf storage); no reference counterpart ------
     def pptrf_batch_strided(self, uplo, n, AP, strideAP, batch, info=None, prec=None):

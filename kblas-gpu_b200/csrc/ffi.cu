@@ -58,6 +58,15 @@ void kblas_gemm_batch_strided_wsquery(kblasHandle_t h, int batchCount) {
   kblasx::gemm_batch_strided_wsquery_core(batchCount, REQ(h));
 }
 void kblas_syrk_batch_wsquery(kblasHandle_t h, int m, int batchCount) { kblasx::syrk_batch_wsquery_core(m, batchCount, REQ(h)); }
+#define KX_INV_WS_C(NAME)                                                                                                   \
+  void kblas_##NAME##_batch_wsquery(kblasHandle_t h, int n, int batchCount) { kblasx::NAME##_batch_wsquery_core(false, n, batchCount, REQ(h)); } \
+  void kblas_##NAME##_batch_strided_wsquery(kblasHandle_t h, int n, int batchCount) {                                       \
+    kblasx::NAME##_batch_wsquery_core(true, n, batchCount, REQ(h));                                                         \
+  }
+KX_INV_WS_C(trtri)
+KX_INV_WS_C(lauum)
+KX_INV_WS_C(potri)
+KX_INV_WS_C(poti)
 #undef REQ
 
 int kblasSset_pointer_1(float **out, const float *in, int lda, long off, long batchCount, void *stream) {

@@ -78,6 +78,11 @@ void posv_batch_wsquery_core(bool strided, int m, int n, char side, int batchCou
 void gemm_batch_offset_wsquery_core(int batchCount, bool offseted, KBlasWorkspaceState *ws);
 void gemm_batch_strided_wsquery_core(int batchCount, KBlasWorkspaceState *ws);
 void syrk_batch_wsquery_core(int m, int batchCount, KBlasWorkspaceState *ws);
+void trmm_batch_wsquery_core(bool strided, int batchCount, char side, int m, int n, KBlasWorkspaceState *ws);
+void lauum_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws);
+void trtri_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws);
+void potri_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws);
+void poti_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws);
 
 int create(KBlasHandle **handle);
 int destroy(KBlasHandle **handle);

@@ -60,6 +60,42 @@ void potrs_batch_wsquery_core(bool strided, int m, int n, int batchCount, KBlasW
     gemm_batch_offset_wsquery_core(batchCount, true, ws);
 }
 
+// reference src/workspace_queries.ch:80-97 (no MAGMA: only the GEMM part of the TRMM recursion)
+void trmm_batch_wsquery_core(bool strided, int batchCount, char side, int m, int n, KBlasWorkspaceState *ws) {
+  if (((side == KBLAS_Right) && (n > 16)) || ((side == KBLAS_Left) && (m > 16))) {
+    if (strided)
+      gemm_batch_strided_wsquery_core(batchCount, ws);
+    else
+      gemm_batch_offset_wsquery_core(batchCount, true, ws);
+  }
+}
+
+// reference src/workspace_queries.ch:127-136
+void lauum_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws) {
+  int n1 = CLOSEST_REG_SIZE(n);
+  trmm_batch_wsquery_core(strided, batchCount, KBLAS_Left, n - n1, n1, ws);
+  syrk_batch_wsquery_core(n1, batchCount, ws);
+}
+
+// reference src/workspace_queries.ch:141-154
+void trtri_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws) {
+  if (n > 16) {
+    int n1 = CLOSEST_REG_SIZE(n);
+    trsm_batch_wsquery_core(strided, batchCount, KBLAS_Left, n - n1, n1, ws);
+    trsm_batch_wsquery_core(strided, batchCount, KBLAS_Right, n - n1, n1, ws);
+  }
+}
+
+// reference src/workspace_queries.ch:176-191
+void potri_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws) {
+  trtri_batch_wsquery_core(strided, n, batchCount, ws);
+  lauum_batch_wsquery_core(strided, n, batchCount, ws);
+}
+void poti_batch_wsquery_core(bool strided, int n, int batchCount, KBlasWorkspaceState *ws) {
+  potrf_batch_wsquery_core(strided, n, batchCount, ws);
+  potri_batch_wsquery_core(strided, n, batchCount, ws);
+}
+
 // reference src/workspace_queries.ch:194-201
 void posv_batch_wsquery_core(bool strided, int m, int n, char side, int batchCount, KBlasWorkspaceState *ws) {
   potrf_batch_wsquery_core(strided, (side == KBLAS_Right) ? n : m, batchCount, ws);

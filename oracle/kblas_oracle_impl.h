@@ -310,6 +310,49 @@ int ORA_(oracle_syrk_batch_strided)(char uplo, char trans, int m, int n, ORA_T a
   return 1;
 }
 
+/* ---- the consumers of the factor: kblas{S,D}{trtri,lauum,potri,poti}_batch_strided
+ * (reference src/batch_triangular/X{trtri,lauum,potri,poti}_batch.cu + drivers: trtri = register kernels up to 16 + two
+ * TRSMs per recursion level, Xtrtri_batch_drivers.cuh:31-125; lauum = register kernels + TRMM + SYRK,
+ * Xlauum_batch_drivers.cuh; potri = trtri then lauum, Xpotri_batch_drivers.cuh; poti = potrf then potri,
+ * Xpoti_batch_drivers.cuh:82-89).  The recursion's operation order goes through cuBLAS GEMM for n > 16, so parity is
+ * tolerance-based; the oracle states the definitions with k-sequential fma chains:
+ *   trtri: column j of X = L^-1 by forward substitution of e_j;  lauum: r_ij = sum_{k>=i} l_ki l_kj, i >= j. */
+static void ORA_(trtri)(int n, ORA_T *A, int lda) {
+  static ORA_T X[256 * 256];
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < n; i++) X[i + (size_t)j * n] = (i == j) ? (ORA_T)1 : (ORA_T)0;
+    for (int k = j; k < n; k++) {
+      X[k + (size_t)j * n] = X[k + (size_t)j * n] / A_(k, k);
+      for (int i = k + 1; i < n; i++) X[i + (size_t)j * n] = ORA_FMA(-A_(i, k), X[k + (size_t)j * n], X[i + (size_t)j * n]);
+    }
+  }
+  for (int j = 0; j < n; j++)
+    for (int i = j; i < n; i++) A_(i, j) = X[i + (size_t)j * n];
+}
+static void ORA_(lauum)(int n, ORA_T *A, int lda) {
+  static ORA_T R[256 * 256];
+  for (int j = 0; j < n; j++)
+    for (int i = j; i < n; i++) {
+      ORA_T s = 0;
+      for (int k = i; k < n; k++) s = ORA_FMA(A_(k, i), A_(k, j), s);
+      R[i + (size_t)j * n] = s;
+    }
+  for (int j = 0; j < n; j++)
+    for (int i = j; i < n; i++) A_(i, j) = R[i + (size_t)j * n];
+}
+/* which: 0 trtri, 1 lauum, 2 potri, 3 poti */
+int ORA_(oracle_inv_batch_strided)(int which, char uplo, char diag, int n, ORA_T *A, int lda, long strideA, int batchCount) {
+  if (uplo == 'U' || diag == 'U') return -2; /* Xtrtri_batch_drivers.cuh:96-99 and siblings */
+  if (n > 256) return -2;
+  for (long b = 0; b < batchCount; b++) {
+    ORA_T *Ab = A + b * strideA;
+    if (which == 3) ORA_(potrf)(n, Ab, lda);
+    if (which == 0 || which == 2 || which == 3) ORA_(trtri)(n, Ab, lda);
+    if (which == 1 || which == 2 || which == 3) ORA_(lauum)(n, Ab, lda);
+  }
+  return 1;
+}
+
 /* ---- packed lower storage (LAPACK ?pptrf, uplo = 'L'): AP[j*n - j(j-1)/2 + (i-j)] = A(i,j), i >= j.
  * The reference has no packed batch routine (its batch_pstrf, src/batch_svd/batch_pstrf.cu:226-246,
  * is pivoted Cholesky on full storage), so the oracle for kblasx?pptrf_batch is DEFINED as: unpack, factor with the

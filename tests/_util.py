@@ -52,6 +52,7 @@ def oracle():
             getattr(_oracle, f"oracle_potrs_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_posv_batch_strided_{s}").argtypes = [c, c, i, i, P, i, l, P, i, l, i]
             getattr(_oracle, f"oracle_pptrf_batch_strided_{s}").argtypes = [c, i, P, l, i]
+            getattr(_oracle, f"oracle_inv_batch_strided_{s}").argtypes = [i, c, c, i, P, i, l, i]
             getattr(_oracle, f"oracle_gemm_batch_strided_{s}").argtypes = [c, c, i, i, i, t, P, i, l, P, i, l, t, P, i, l, i]
             getattr(_oracle, f"oracle_syrk_batch_strided_{s}").argtypes = [c, c, i, i, t, P, i, l, t, P, i, l, i]
             getattr(_oracle, f"oracle_potrs_left_batch_strided_{s}").argtypes = [i, i, P, i, l, P, i, l, i]
@@ -123,6 +124,13 @@ def oracle_syrk(uplo, trans, m, n, alpha, A, beta, Cm):
     _, ncc, ldc = Cm.shape
     f = getattr(oracle(), f"oracle_syrk_batch_strided_{SUFFIX[_dt(Cm)]}")
     return f(uplo.encode(), trans.encode(), m, n, alpha, _np_ptr(A), lda, nca * lda, beta, _np_ptr(Cm), ldc, ncc * ldc, b)
+
+
+def oracle_inv(which, n, A, uplo="L", diag="N"):
+    """in place on A[(batch, ncols, lda)]: which = 'trtri' | 'lauum' | 'potri' | 'poti' (lower triangle)"""
+    b, nc, lda = A.shape
+    f = getattr(oracle(), f"oracle_inv_batch_strided_{SUFFIX[_dt(A)]}")
+    return f({"trtri": 0, "lauum": 1, "potri": 2, "poti": 3}[which], uplo.encode(), diag.encode(), n, _np_ptr(A), lda, nc * lda, b)
 
 
 def oracle_posv_left(m, n, A, B):
