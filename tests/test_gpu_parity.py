@@ -294,6 +294,15 @@ def test_potrf_host_pipeline(env, p, n, lda, extra, mode, monkeypatch):
         untouched = (j // 8) > (i // 8)          # as_mats gives [b, row, col]
         assert (M[:, untouched] == 9.5).all()
     assert h.potrf_batch_strided_host("U", n, src, out, lda, stride, batch) == kb.KBLAS_NotImplemented
+    if mode == "full":
+        # a caller with stride > lda*n owns nothing behind the last matrix -- the last chunk must stop at
+        # the last element of the last matrix (host buffers of exactly the minimal strided size, guard words behind them)
+        need = (batch - 1) * stride + lda * (n - 1) + n
+        buf = np.full(need + 64, 123.0, dtype=dt)
+        buf[:need] = A0.flatten()[:need]
+        assert h.potrf_batch_strided_host("L", n, buf, buf, lda, stride, batch) == kb.KBLAS_Success
+        assert np.array_equal(buf[:need], want.flatten()[:need])
+        assert (buf[need:] == 123.0).all(), "wrote past the last element of the last matrix"
 
 
 # =============================================================================================
