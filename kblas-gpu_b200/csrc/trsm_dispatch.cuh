@@ -36,9 +36,15 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   constexpr int WARPS = LEFT ? 2 : 4;  // side L carries a transpose tile per problem: 2-warp CTAs keep 3 CTAs per SM
   const int slabs = (vec + 31) / 32;
   const long tasks = (long)batchCount * slabs;
-  const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
+  long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
   const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
+  // persistent: one resident wave, every warp pulls its next task into L2 while it works on the current one
+  // (KBLAS_B200_VARIANT=40: one task pair per warp, the round-1 launch shape, for A/B runs)
+  if (h->variant_override != 40) {
+    const long wave = (long)h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, 1);
+    if (grid > wave) grid = wave;
+  }
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
