@@ -70,47 +70,14 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
   constexpr int TS = TriDualSmem<T, NP, LEFT>::tile_stride;
   T *tile = reinterpret_cast<T *>(smem_raw) + warp * TriDualSmem<T, NP, LEFT>::per_warp + 2 * FSZ + g * TriDualSmem<T, NP, LEFT>::tile;
 
-  // persistent warps: with a grid smaller than the task count every warp walks tasks t0, t0 + stride, ... and pulls the
-  // operands of its NEXT task into L2 while it substitutes the current one (launcher: trsm_dispatch.cuh)
   const long ntask = (long)batchCount * slabs;
-  const long tstride = (long)gridDim.x * WARPS * 2;
-  for (long t0 = ((long)blockIdx.x * WARPS + warp) * 2; t0 < ntask; t0 += tstride) {
-  const long task = t0 + g;  // (matrix, 32-vector slab)
+  const long task = ((long)blockIdx.x * WARPS + warp) * 2 + g;  // (matrix, 32-vector slab)
   const bool live = task < ntask;
   const long tsafe = live ? task : ntask - 1;
   const long mat = tsafe / slabs;
   const int v0 = (int)(tsafe % slabs) * 32;
   const T *__restrict__ A = Aref.at(mat);
   T *__restrict__ B = Bref.at(mat);
-  if (t0 + tstride + g < ntask) {
-    const long nt = t0 + tstride + g;
-    const long nmat = nt / slabs;
-    const int nv0 = (int)(nt % slabs) * 32;
-    const char *pa = reinterpret_cast<const char *>(Aref.at(nmat));
-    const char *pb = reinterpret_cast<const char *>(Bref.at(nmat));
-    constexpr int ES = (int)sizeof(T);
-    // factor: the lines of column c that hold rows c .. NP-1;  B: the lines of my 32 vectors (side R: 32 rows of every
-    // column; side L: NP rows of 32 columns)
-#pragma unroll
-    for (int c = lg; c < NP; c += 16) {
-      const long lo = ((long)c * lda + c) * ES, hi = ((long)c * lda + NP - 1) * ES;
-      for (long o = lo & ~127L; o <= hi; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
-    }
-    if (!LEFT) {
-#pragma unroll
-      for (int c = lg; c < NP; c += 16) {
-        const long lo = ((long)c * ldb + nv0) * ES, hi = lo + 31 * ES;
-        for (long o = lo & ~127L; o <= hi; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
-      }
-    } else {
-#pragma unroll
-      for (int c = lg; c < 32; c += 16) {
-        const long lo = ((long)(nv0 + c) * ldb) * ES, hi = lo + (NP - 1) * ES;
-        if (nv0 + c < vec)
-          for (long o = lo & ~127L; o <= hi; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
-      }
-    }
-  }
 
   // ---- factor: global -> shared, asynchronously; sectors wholly above the diagonal are skipped ----------
 #pragma unroll
@@ -254,8 +221,6 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
       }
     }
   }
-  __syncwarp();  // the staged factor / tile are overwritten by the next task
-  }  // persistent task loop
 }
 
 }  // namespace kblasx

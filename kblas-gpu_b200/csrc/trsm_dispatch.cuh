@@ -36,18 +36,9 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   constexpr int WARPS = LEFT ? 2 : 4;  // side L carries a transpose tile per problem: 2-warp CTAs keep 3 CTAs per SM
   const int slabs = (vec + 31) / 32;
   const long tasks = (long)batchCount * slabs;
-  long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
+  const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
   const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
-  // persistent (one resident wave, every warp pulls its next task into L2 while it works on the current one) only where it
-  // measured faster: fp64 k = 16 (B200, 2^20 problems, persistent vs one task pair per warp: dpotrs 1.46 vs 1.99 ms, dtrsm
-  // R/N 0.99 vs 1.18, R/T 1.11 vs 1.50; but k = 32: dpotrs 5.63 vs 4.46, dtrsm R 4.44 vs 3.74; fp32 k = 16: 0.68 vs 0.63).
-  // KBLAS_B200_VARIANT = 40 / 41 force the non-persistent / persistent launch shape for A/B runs.
-  const bool persist = h->variant_override == 41 || (h->variant_override != 40 && sizeof(T) == 8 && NP == 16);
-  if (persist) {
-    const long wave = (long)h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, 1);
-    if (grid > wave) grid = wave;
-  }
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
   kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
   h->note_launch(name);
