@@ -301,8 +301,12 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
       if (DW > 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * DW) : "memory");
       else __syncwarp();
       KX_T(8 + 8 * J + 4);  // diagonal block updated
-      if (warp == 0) factor_diag(Jn);
-      else offdiag_strips(Jn);
+      if (warp == 0) {
+        factor_diag(Jn);
+        if (WARPS == 1) offdiag_strips(Jn);  // one warp per matrix: nobody else to take them
+      } else {
+        offdiag_strips(Jn);
+      }
     } else {
       offdiag_strips(Jn);
     }

@@ -99,7 +99,8 @@ static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
     // overlap the 32-step dependent chains of the diagonal factorisation (7-10K cycles) and of the row solves (4-6K cycles
     // per block) with (profiles/r02_smem_phase_trace.txt), which eight independent matrices per SM overlap for free.  Opt-in.
     const int v = h->variant_override;
-    if (n <= 256 && v >= 31 && v <= 35) {
+    if (n <= 256 && v >= 31 && v <= 36) {
+      if (v == 36) return launch_potrf_smem<1, 8, STRIDED>(h, "potrf_smem<W=1>", n, A, lda, batchCount, info);
       if (v == 31) return launch_potrf_smem<2, 8, STRIDED>(h, "potrf_smem<W=2,MB=8>", n, A, lda, batchCount, info);
       if (v == 34) return launch_potrf_smem<2, 4, STRIDED>(h, "potrf_smem<W=2,MB=4>", n, A, lda, batchCount, info);
       if (v == 32) return launch_potrf_smem<4, 4, STRIDED>(h, "potrf_smem<W=4,MB=4>", n, A, lda, batchCount, info);

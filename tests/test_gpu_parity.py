@@ -115,7 +115,7 @@ def test_potrf_strided_large_n(env, p, n):
     _check_potrf(A0, dA.cpu().numpy(), n, dt, Lref=Lo)
 
 
-@pytest.mark.parametrize("variant", [-1, 31, 32, 33, 34, 35])
+@pytest.mark.parametrize("variant", [-1, 31, 32, 33, 34, 35, 36])
 def test_dpotrf_large_n_kernel_variants(variant, monkeypatch):
     """fp64, 32 < n <= 256: the one-warp-per-matrix DMMA kernel (default) and the opt-in shared-memory resident kernel
     (31 / 32 / 33 = 2 / 4 / 8 warps per matrix): ragged n, padded lda, strided and pointer array, 16-byte aligned and
@@ -144,7 +144,7 @@ def test_dpotrf_large_n_kernel_variants(variant, monkeypatch):
                 rc = h.potrf_batch("L", n, _ptrs(torch, dA, off, perm, n * lda, 8), lda, batch, None, prec="D")
             torch.cuda.synchronize()
             assert rc == kb.KBLAS_Success
-            want = "potrf_panel_dmma" if variant < 0 else "potrf_smem" + {31: "<W=2,MB=8>", 32: "<W=4,MB=4>", 33: "<W=8>", 34: "<W=2,MB=4>", 35: "<W=4,MB=2>"}[variant]
+            want = "potrf_panel_dmma" if variant < 0 else "potrf_smem" + {31: "<W=2,MB=8>", 32: "<W=4,MB=4>", 33: "<W=8>", 34: "<W=2,MB=4>", 35: "<W=4,MB=2>", 36: "<W=1>"}[variant]
             assert want in h.last_kernel, h.last_kernel
             got = dA[off:off + A0.size].cpu().numpy().reshape(A0.shape)
             _check_potrf(A0, got, n, dt, Lref=Lo)
