@@ -116,7 +116,7 @@ potrf_smem_kernel(const int n, BatchRef<double, STRIDED> Aref, const int lda, co
 
   // the slot table goes to shared memory (indexing the kernel parameter dynamically would copy it to local memory)
   unsigned char *const slot_tab = reinterpret_cast<unsigned char *>(invd + NB);
-  if (tid < 64) slot_tab[tid] = plan.slot[tid >> 3][tid & 7];
+  for (int i = tid; i < 64; i += THREADS) slot_tab[i] = plan.slot[i >> 3][i & 7];
   __syncthreads();
   auto blk = [&](int I, int K) -> double * { return blocks + (int)slot_tab[I * 8 + K] * BLK; };
 
