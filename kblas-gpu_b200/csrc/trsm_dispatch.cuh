@@ -9,6 +9,7 @@
 #include "kernels/trsm_blocked.cuh"
 #include "kernels/trsm_reg.cuh"
 #include "kernels/trsm_dual.cuh"
+#include "kernels/trsm_left_vec.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -44,6 +45,36 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
+}
+
+// side L, strided, everything 16-byte aligned: 16-byte accesses only (kernels/trsm_left_vec.cuh)
+template <typename T>
+static bool tri_left_vec_ok(int k, const BatchRef<const T, true> &A, int lda, const BatchRef<T, true> &B, int ldb) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  return k % VW == 0 && lda % VW == 0 && ldb % VW == 0 && A.stride % VW == 0 && B.stride % VW == 0 &&
+         ((unsigned long long)A.base | (unsigned long long)B.base) % 16 == 0;
+}
+template <typename T>
+static bool tri_left_vec_ok(int, const BatchRef<const T, false> &, int, const BatchRef<T, false> &, int) { return false; }
+
+template <typename T, int NP, int OP>
+static int launch_tri_left_vec(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, true> A, int lda,
+                               BatchRef<T, true> B, int ldb, int batchCount) {
+  constexpr int WARPS = TriLeftVecSmem<T, NP>::warps, MINB = TriLeftVecSmem<T, NP>::ctas_per_sm;
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  const size_t smem = (size_t)WARPS * TriLeftVecSmem<T, NP>::per_warp * sizeof(T);
+  auto kern = tri_left_vec_kernel<T, NP, OP, WARPS, MINB>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+template <typename T, int NP, int OP>
+static int launch_tri_left_vec(KBlasHandle *, const char *, int, int, T, BatchRef<const T, false>, int, BatchRef<T, false>, int, int) {
+  return KBLAS_UnknownError;  // never selected: tri_left_vec_ok is false for pointer arrays
 }
 
 // k <= 16 and vec <= 16: register-resident, 2 / 4 problems per warp (kernels/trsm_reg.cuh)
@@ -109,6 +140,22 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
   // measured (B200, 2^20 problems, side L): dual vs one-vector kernel  fp64 k=32 4.7-5.1 vs 5.1-5.4 ms, k=24 3.0-3.4 vs
   // 3.6-3.9; fp32 k=24 2.07 vs 2.35 but k=32 2.96-3.07 vs 2.77-2.83 -> fp32 k=32 side L stays on the older kernel
+  if constexpr (LEFT) {
+    // 16-byte kernel vs the element-wise ones, measured on B200 (2^20 problems, vec = k, ms; profiles/r02_trsm_left_vec.txt):
+    //   fp64 k=32  trsm N 3.93 vs 4.70, T 3.78 vs 4.81, potrs 5.65 vs 6.47     fp32 k=32  2.18 vs 2.77, 1.82 vs 2.68, 2.72 vs 3.62
+    //   fp64 k=24  2.78 vs 2.93, 2.58 vs 3.01, potrs 3.92 vs 3.51 (stays)      fp32 k=24  1.27 vs 1.65, 1.24 vs 1.68, 1.77 vs 2.18
+    //   k=16: only the fused potrs wins (16 vectors: fp64 1.59 vs 2.54, fp32 0.91 vs 1.49); k=8 and few vectors (idle
+    //   lanes) stay on the register kernels.  Variant 40 forces it wherever it is eligible, 41 switches it off.
+    const int vo = h->variant_override;
+    const bool pays = k > 16 ? (vec > 16 && !(sizeof(T) == 8 && OP == TRI_BOTH && k <= 24)) : (k > 8 && vec > 8 && OP == TRI_BOTH);
+    const bool want = vo == 40 || (vo != 41 && pays);
+    if (want && tri_left_vec_ok<T>(k, A, lda, B, ldb)) {
+      if (k <= 8) return launch_tri_left_vec<T, 8, OP>(h, "tri_left_vec<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+      if (k <= 16) return launch_tri_left_vec<T, 16, OP>(h, "tri_left_vec<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+      if (k <= 24) return launch_tri_left_vec<T, 24, OP>(h, "tri_left_vec<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);
+      return launch_tri_left_vec<T, 32, OP>(h, "tri_left_vec<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    }
+  }
   const bool dual_ok = !LEFT || !(sizeof(T) == 4 && k == 32);
   if (dual_ok) {
     // k = 16 with <= 16 vectors leaves the second vector of every lane idle and still wins on side R (measured, ms per

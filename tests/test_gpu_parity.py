@@ -355,6 +355,60 @@ def test_trsm_large_k(env, p, side, trans, k, other):
     assert np.abs(dB.cpu().numpy() - Bo).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo).max())
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("op", ["N", "T", "potrs"])
+@pytest.mark.parametrize("k,vec,pad", [(32, 32, 0), (32, 100, 1), (24, 24, 0), (24, 40, 2), (16, 32, 1), (16, 17, 0), (8, 33, 1),
+                                         (20, 32, 1), (28, 9, 0), (12, 64, 0), (4, 5, 1)])
+def test_left_side_16_byte_kernel(p, op, k, vec, pad, monkeypatch):
+    """kernels/trsm_left_vec.cuh (strided side L, every global access 16 bytes wide): forced on with variant 40 wherever
+    its alignment conditions hold, for every factor order / ragged slab / padded leading dimension it claims, against the
+    oracle; plus the fallback when the operands are NOT 16-byte aligned (same numbers from the element-wise kernels)."""
+    import torch
+    monkeypatch.setenv("KBLAS_B200_VARIANT", "40")
+    kb = U.kblas()
+    h = kb.Handle()
+    try:
+        dt = DT[p]
+        vw = 16 // np.dtype(dt).itemsize
+        batch, alpha = 37, 0.28
+        lda, ldb = k + pad * vw, k + 2 * pad * vw
+        A = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=k + 7)
+        assert U.oracle_potrf(A, k) == 1                # a real Cholesky factor in the lower triangle
+        B0 = U.rand_batch(batch, k, vec, ld=ldb, dtype=dt, seed=k * 100 + vec)
+        Bo = B0.copy()
+        if op == "potrs":                               # (L L^T) X = B: the restated trsm L,L,N then L,L,T
+            U.oracle_trsm("L", "L", "N", "N", k, vec, 1.0, A, Bo)
+            U.oracle_trsm("L", "L", "T", "N", k, vec, 1.0, A, Bo)
+        else:
+            U.oracle_trsm("L", "L", op, "N", k, vec, alpha, A, Bo)
+        tol = 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :k]).max())
+
+        def run(dA, dB, a_off, b_off):
+            Av, Bv = dA[a_off:], dB[b_off:]
+            if op == "potrs":
+                return h.potrs_batch_strided("L", "L", k, vec, Av, lda, k * lda, Bv, ldb, vec * ldb, batch)
+            return h.trsm_batch_strided("L", "L", op, "N", k, vec, alpha, Av, lda, k * lda, Bv, ldb, vec * ldb, batch)
+
+        # aligned operands: the 16-byte kernel
+        dA, dB = _dev(torch, A).flatten(), _dev(torch, B0).flatten()
+        assert run(dA, dB, 0, 0) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        assert h.last_kernel.startswith("tri_left_vec"), h.last_kernel
+        got = dB.cpu().numpy().reshape(B0.shape)
+        assert np.abs(got[:, :, :k] - Bo[:, :, :k]).max() <= tol
+        assert np.array_equal(got[:, :, k:], B0[:, :, k:]), "ldb padding untouched"
+        assert np.array_equal(dA.cpu().numpy().reshape(A.shape), A), "the factor is read-only"
+        # B one element past a 16-byte boundary: not eligible, same result from the element-wise kernels
+        dB1 = _slack_copy(torch, B0, 1)
+        assert run(dA, dB1, 0, 1) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        assert not h.last_kernel.startswith("tri_left_vec"), h.last_kernel
+        got1 = dB1.cpu().numpy()[1:1 + B0.size].reshape(B0.shape)
+        assert np.abs(got1[:, :, :k] - Bo[:, :, :k]).max() <= tol
+    finally:
+        h.destroy()
+
+
 def _slack_copy(torch, a, off):
     """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
     `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""

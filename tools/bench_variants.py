@@ -100,6 +100,7 @@ def main():
                     h = kb.Handle()
                     for name, fn in (
                         ("potrs_R", lambda: h.potrs_batch_strided("R", "L", m, n, L, n, n * n, B, m, m * n, batch)),
+                        ("potrs_L", lambda: h.potrs_batch_strided("L", "L", n, m, L, n, n * n, B, n, m * n, batch)),
                         ("trsm_LLN", lambda: h.trsm_batch_strided("L", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
                         ("trsm_LLT", lambda: h.trsm_batch_strided("L", "L", "T", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
                         ("trsm_RLN", lambda: h.trsm_batch_strided("R", "L", "N", "N", m, n, 0.28, L, n, n * n, B, m, m * n, batch)),
