@@ -43,6 +43,9 @@ __device__ __forceinline__ void stg_vec_stream(float *p, const float (&v)[4]) {
                : "memory");
 }
 
+#ifndef KX_TLV_FENCE_F64
+#define KX_TLV_FENCE_F64 2
+#endif
 #ifndef KX_TLV_MAXB
 #define KX_TLV_MAXB 6  // CTAs per SM: 6 x 4 warps leave 80 registers per thread
 #endif
@@ -57,6 +60,52 @@ struct TriLeftVecSmem {
   static_assert((NP * sizeof(T)) % 16 == 0, "factor columns and the tile must stay 16-byte aligned");
 };
 
+// forward / backward substitution of one NP-vector per lane against the staged factor (column-major Ls, reciprocal diagonal
+// invd): broadcast LDS.128 = VW factor entries for all 32 lanes
+template <typename T, int NP, int OP>
+__device__ __forceinline__ void tri_vec_substitute(T (&x)[NP], const T *Ls, const T *invd) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  constexpr int NV = NP / VW;
+  constexpr int FENCE = sizeof(T) == 8 ? 4 : 8;    // columns between scheduling fences (bounds ptxas' LDS look-ahead), backward
+  constexpr int FENCE_F = sizeof(T) == 8 ? KX_TLV_FENCE_F64 : 4;  // forward: every hoisted column costs NP registers
+  if (OP == TRI_FORWARD || OP == TRI_BOTH) {
+    T dv[VW];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (j % FENCE_F == 0) sched_fence();
+      if (j % VW == 0) lds_vec(dv, invd + j);
+      x[j] *= dv[j % VW];
+      const T nx = -x[j];
+#pragma unroll
+      for (int v = (j + 1) / VW; v < NV; ++v) {
+        T c[VW];
+        lds_vec(c, Ls + v * VW + j * NP);
+#pragma unroll
+        for (int e = 0; e < VW; ++e)
+          if (v * VW + e > j) x[v * VW + e] = fma_t(nx, c[e], x[v * VW + e]);
+      }
+    }
+  }
+  if (OP == TRI_BACKWARD || OP == TRI_BOTH) {
+    T dv[VW];
+#pragma unroll
+    for (int j = NP - 1; j >= 0; --j) {
+      if ((NP - 1 - j) % FENCE == 0) sched_fence();
+      if (j % VW == VW - 1) lds_vec(dv, invd + j - (VW - 1));
+      T acc[4] = {x[j], T(0), T(0), T(0)};
+#pragma unroll
+      for (int v = (j + 1) / VW; v < NV; ++v) {
+        T c[VW];
+        lds_vec(c, Ls + v * VW + j * NP);
+#pragma unroll
+        for (int e = 0; e < VW; ++e)
+          if (v * VW + e > j) acc[(v * VW + e) & 3] = fma_t(-x[v * VW + e], c[e], acc[(v * VW + e) & 3]);
+      }
+      x[j] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * dv[j % VW];
+    }
+  }
+}
+
 // k = order of the factor (a multiple of 16 / sizeof(T), <= NP), vec = columns of B.  lda, ldb, the batch strides and both
 // base pointers are multiples of 16 bytes (the launcher checks).
 template <typename T, int NP, int OP, int WARPS, int MINB>
@@ -66,7 +115,6 @@ tri_left_vec_kernel(const int k, const int vec, const T alpha, const T *__restri
   constexpr int VW = TriLeftVecSmem<T, NP>::VW;
   constexpr int NV = NP / VW;
   constexpr int TS = TriLeftVecSmem<T, NP>::TS;
-  constexpr int FENCE = sizeof(T) == 8 ? 4 : 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -109,42 +157,7 @@ tri_left_vec_kernel(const int k, const int vec, const T alpha, const T *__restri
     for (int e = 0; e < VW; ++e) x[q * VW + e] = alpha * c[e];
   }
 
-  if (OP == TRI_FORWARD || OP == TRI_BOTH) {
-    T dv[VW];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      if (j % 4 == 0) sched_fence();
-      if (j % VW == 0) lds_vec(dv, invd + j);
-      x[j] *= dv[j % VW];
-      const T nx = -x[j];
-#pragma unroll
-      for (int v = (j + 1) / VW; v < NV; ++v) {
-        T c[VW];
-        lds_vec(c, Ls + v * VW + j * NP);
-#pragma unroll
-        for (int e = 0; e < VW; ++e)
-          if (v * VW + e > j) x[v * VW + e] = fma_t(nx, c[e], x[v * VW + e]);
-      }
-    }
-  }
-  if (OP == TRI_BACKWARD || OP == TRI_BOTH) {
-    T dv[VW];
-#pragma unroll
-    for (int j = NP - 1; j >= 0; --j) {
-      if ((NP - 1 - j) % FENCE == 0) sched_fence();
-      if (j % VW == VW - 1) lds_vec(dv, invd + j - (VW - 1));
-      T acc[4] = {x[j], T(0), T(0), T(0)};
-#pragma unroll
-      for (int v = (j + 1) / VW; v < NV; ++v) {
-        T c[VW];
-        lds_vec(c, Ls + v * VW + j * NP);
-#pragma unroll
-        for (int e = 0; e < VW; ++e)
-          if (v * VW + e > j) acc[(v * VW + e) & 3] = fma_t(-x[v * VW + e], c[e], acc[(v * VW + e) & 3]);
-      }
-      x[j] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * dv[j % VW];
-    }
-  }
+  tri_vec_substitute<T, NP, OP>(x, Ls, invd);
 
   // ---- back through the tile, then 16-byte streaming stores ------------------------------------------------------------
 #pragma unroll
@@ -165,6 +178,60 @@ tri_left_vec_kernel(const int k, const int vec, const T alpha, const T *__restri
       stg_vec_stream(Bs + (long)c * ldb + r0, o);
     }
   }
+}
+
+// ---- side R: vector = row of B, lanes = consecutive rows, so B needs no staging at all; only the factor goes through
+// shared memory (16-byte cp.async).  One vector per lane keeps the kernel at ~100 registers: 16 warps per SM.
+template <typename T, int NP>
+struct TriRightVecSmem {
+  static constexpr int per_warp = NP * NP + NP;
+  static constexpr int warps = 4;
+  static constexpr int ctas_per_sm = 4;
+};
+
+template <typename T, int NP, int OP, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+tri_right_vec_kernel(const int k, const int vec, const T alpha, const T *__restrict__ A0, const int lda, const long strideA,
+                     T *__restrict__ B0, const int ldb, const long strideB, const int batchCount, const int slabs) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  constexpr int NV = NP / VW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T *Ls = reinterpret_cast<T *>(smem_raw) + warp * TriRightVecSmem<T, NP>::per_warp;
+  T *invd = Ls + NP * NP;
+
+  const long task = (long)blockIdx.x * WARPS + warp;  // (matrix, 32-row slab)
+  if (task >= (long)batchCount * slabs) return;        // warp-uniform
+  const long mat = task / slabs;
+  const int my = (int)(task % slabs) * 32 + lane;      // my row of B
+  const T *__restrict__ A = A0 + mat * strideA;
+  T *__restrict__ B = B0 + mat * strideB;
+
+#pragma unroll
+  for (int i0 = 0; i0 < NP * NV; i0 += 32) {
+    const int i = i0 + lane, c = i / NV, r0 = (i % NV) * VW;
+    if ((NP * NV) % 32 == 0 || c < NP)
+      cp_async16_if(Ls + c * NP + r0, A + (long)c * lda + r0, c < k && r0 < k && r0 + VW - 1 >= c);
+  }
+  T x[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    x[j] = T(0);
+    ldg_stream_if(x[j], B + my + (long)j * ldb, my < vec && j < k);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  if (lane < NP) invd[lane] = lane < k ? T(1) / Ls[lane + lane * NP] : T(1);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NP; ++j) x[j] *= alpha;
+
+  tri_vec_substitute<T, NP, OP>(x, Ls, invd);
+
+  T *Bs = launder(B);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) stg_stream_if(Bs + my + (long)j * ldb, x[j], my < vec && j < k);
 }
 
 }  // namespace kblasx

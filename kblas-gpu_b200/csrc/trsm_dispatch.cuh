@@ -77,6 +77,35 @@ static int launch_tri_left_vec(KBlasHandle *, const char *, int, int, T, BatchRe
   return KBLAS_UnknownError;  // never selected: tri_left_vec_ok is false for pointer arrays
 }
 
+// side R, strided, 16-byte aligned factor: one vector per lane, factor staged with 16-byte cp.async (kernels/trsm_left_vec.cuh)
+template <typename T>
+static bool tri_right_vec_ok(int k, const BatchRef<const T, true> &A, int lda) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  return k % VW == 0 && lda % VW == 0 && A.stride % VW == 0 && (unsigned long long)A.base % 16 == 0;
+}
+template <typename T>
+static bool tri_right_vec_ok(int, const BatchRef<const T, false> &, int) { return false; }
+
+template <typename T, int NP, int OP>
+static int launch_tri_right_vec(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, true> A, int lda,
+                                BatchRef<T, true> B, int ldb, int batchCount) {
+  constexpr int WARPS = TriRightVecSmem<T, NP>::warps, MINB = TriRightVecSmem<T, NP>::ctas_per_sm;
+  const int slabs = (vec + 31) / 32;
+  const long tasks = (long)batchCount * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  const size_t smem = (size_t)WARPS * TriRightVecSmem<T, NP>::per_warp * sizeof(T);
+  auto kern = tri_right_vec_kernel<T, NP, OP, WARPS, MINB>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+template <typename T, int NP, int OP>
+static int launch_tri_right_vec(KBlasHandle *, const char *, int, int, T, BatchRef<const T, false>, int, BatchRef<T, false>, int, int) {
+  return KBLAS_UnknownError;
+}
+
 // k <= 16 and vec <= 16: register-resident, 2 / 4 problems per warp (kernels/trsm_reg.cuh)
 template <typename T, int NP, int GP, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_reg(KBlasHandle *h, const char *name, int k, int vec, T alpha, BatchRef<const T, STRIDED> A,
@@ -155,6 +184,14 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
       if (k <= 24) return launch_tri_left_vec<T, 24, OP>(h, "tri_left_vec<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);
       return launch_tri_left_vec<T, 32, OP>(h, "tri_left_vec<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
     }
+  }
+  if constexpr (!LEFT && OP == TRI_BACKWARD && sizeof(T) == 8) {
+    // side R, X L = alpha B in fp64 with a full 32-row slab: one vector per lane at 16 warps per SM beats the two-vector
+    // kernel (2^20 problems, k = vec = 32: 3.52 vs 4.06 ms = 0.94 vs 0.81 of the HBM roofline).  The forward form of the
+    // same kernel spills at 128 registers and loses (4.12 vs 3.91), fp32 loses (2.49 vs 2.38), fewer than 32 rows leave
+    // lanes idle (k = vec = 24: 2.47 vs 2.14): those stay where they were.  Variant 43 switches it off.
+    if (k > 24 && vec >= 32 && h->variant_override != 43 && tri_right_vec_ok<T>(k, A, lda))
+      return launch_tri_right_vec<T, 32, OP>(h, "tri_right_vec<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
   }
   const bool dual_ok = !LEFT || !(sizeof(T) == 4 && k == 32);
   if (dual_ok) {

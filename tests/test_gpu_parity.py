@@ -409,6 +409,38 @@ def test_left_side_16_byte_kernel(p, op, k, vec, pad, monkeypatch):
         h.destroy()
 
 
+@pytest.mark.parametrize("k,vec,pad", [(32, 32, 0), (32, 100, 1), (28, 45, 1), (26, 32, 0)])
+def test_right_side_one_vector_kernel(env, k, vec, pad):
+    """kernels/trsm_left_vec.cuh, tri_right_vec: dtrsm R,L,N (X L = alpha B) with a 16-byte aligned strided factor of order
+    25..32 and at least 32 rows -- picked by default; against the oracle, and against the two-vector kernel it replaces
+    (B one element off a 16-byte boundary changes nothing for side R, an odd lda makes the factor ineligible)."""
+    kb, h, torch = env
+    dt = np.float64
+    batch, alpha = 41, 0.28
+    lda, ldb = k + 2 * pad, vec + 3 * pad
+    A = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=k + 11)
+    assert U.oracle_potrf(A, k) == 1
+    B0 = U.rand_batch(batch, vec, k, ld=ldb, dtype=dt, seed=k * 100 + vec)
+    Bo = B0.copy()
+    U.oracle_trsm("R", "L", "N", "N", vec, k, alpha, A, Bo)
+    tol = 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :vec]).max())
+    dA, dB = _dev(torch, A), _dev(torch, B0)
+    assert h.trsm_batch_strided("R", "L", "N", "N", vec, k, alpha, dA, lda, k * lda, dB, ldb, k * ldb, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert h.last_kernel.startswith("tri_right_vec"), h.last_kernel
+    got = dB.cpu().numpy()
+    assert np.abs(got[:, :, :vec] - Bo[:, :, :vec]).max() <= tol
+    assert np.array_equal(got[:, :, vec:], B0[:, :, vec:]), "ldb padding untouched"
+    assert np.array_equal(dA.cpu().numpy(), A), "the factor is read-only"
+    # factor one element off a 16-byte boundary: the two-vector / element-wise kernels, same numbers
+    dA1 = _slack_copy(torch, A, 1)
+    dB.copy_(_dev(torch, B0))
+    assert h.trsm_batch_strided("R", "L", "N", "N", vec, k, alpha, dA1[1:], lda, k * lda, dB, ldb, k * ldb, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert not h.last_kernel.startswith("tri_right_vec"), h.last_kernel
+    assert np.abs(dB.cpu().numpy()[:, :, :vec] - Bo[:, :, :vec]).max() <= tol
+
+
 def _slack_copy(torch, a, off):
     """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
     `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""
