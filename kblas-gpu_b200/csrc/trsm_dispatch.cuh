@@ -10,6 +10,7 @@
 #include "kernels/trsm_reg.cuh"
 #include "kernels/trsm_dual.cuh"
 #include "kernels/trsm_left_vec.cuh"
+#include "kernels/trsm_mma.cuh"
 #include "tri_batch.h"
 
 namespace kblasx {
@@ -154,9 +155,33 @@ static int launch_tri_blocked_gp(KBlasHandle *h, const char *name, int k, int ve
   return KBLAS_Success;
 }
 
+// k > 32, side R, fp64: the off-diagonal products on DMMA (kernels/trsm_mma.cuh)
+template <int OP, int GP, bool STRIDED>
+static int launch_tri_mma(KBlasHandle *h, const char *name, int k, int vec, double alpha, BatchRef<const double, STRIDED> A, int lda,
+                          BatchRef<double, STRIDED> B, int ldb, int batchCount) {
+  constexpr int WARPS = 4, MPW = 32 / GP;
+  const int slabs = (GP == 32) ? (vec + 31) / 32 : 1;
+  const long tasks = (((long)batchCount + MPW - 1) / MPW) * slabs;
+  const long grid = (tasks + WARPS - 1) / WARPS;
+  const size_t smem = (size_t)WARPS * TriMmaSmem::per_warp * sizeof(double);
+  auto kern = tri_solve_mma_kernel<OP, GP, WARPS, STRIDED>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  h->note_launch(name);
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                               BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  if constexpr (sizeof(T) == 8 && !LEFT) {
+    // variant 44 keeps the FMA kernels (A/B)
+    if (h->variant_override != 44 && vec > 8) {
+      if (vec <= 16) return launch_tri_mma<OP, 16, STRIDED>(h, "tri_mma<GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+      return launch_tri_mma<OP, 32, STRIDED>(h, "tri_mma<GP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    }
+  }
   if (vec <= 8)
     return launch_tri_blocked_gp<T, LEFT, OP, 8, STRIDED>(h, "tri_blocked<GP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
   if (vec <= 16)

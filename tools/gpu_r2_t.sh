@@ -1,0 +1,4 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out/r2t
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "large_k or posv or potrs or random_shapes or config4 or live_large" > gpurun_out/r2t/pytest.log 2>&1; tail -5 gpurun_out/r2t/pytest.log
+timeout 900 python tools/bench_variants.py -1,44 large > gpurun_out/r2t/bench_large.jsonl 2> gpurun_out/r2t/bench_large.err; tail -2 gpurun_out/r2t/bench_large.err
