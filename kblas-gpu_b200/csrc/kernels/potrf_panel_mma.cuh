@@ -67,6 +67,53 @@ __device__ __forceinline__ void panel_update_mma(double *acc_w, const int LD, co
   for (int rb = 0; rb < 4; ++rb)
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
+#ifndef KX_PANEL_NO_PAIRED_LOADS
+  if (((reinterpret_cast<unsigned long long>(A) | ((unsigned long long)(lda & 1) << 3)) & 15) == 0 && ((wrow0 | j0) & 1) == 0) {
+    // 16-byte aligned columns: a lane fetches TWO consecutive rows with one 16-byte load and feeds them to two different
+    // fragment tiles -- tile (p, h) holds rows 16 p + 2 fr + h instead of 8 (2 p + h) + fr.  Any bijection between fragment
+    // slots and rows is a valid m8n8k4 operand as long as the accumulator is written back with the same one; this one makes
+    // every load instruction cover 128 contiguous bytes per column (8 lanes x 16 B) instead of 64, with half as many loads.
+    int ar[2], br[2];
+    // pairs that start beyond the last row read the last pair instead; a pair may END one row past it when n is odd: that
+    // element is the head of the next column (k < j0 <= n - 1, so it is inside the matrix) and only reaches accumulator
+    // rows / columns >= n, which nobody uses
+    const int last2 = (n - 1) & ~1;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      ar[p] = wrow0 + 16 * p + 2 * fr;
+      ar[p] = ar[p] < n ? ar[p] : last2;
+      br[p] = j0 + 16 * p + 2 * fr;
+      br[p] = br[p] < n ? br[p] : last2;
+    }
+    const double *col = A + (long)fk * lda;
+#pragma unroll 4
+    for (int k = 0; k < j0; k += 4) {
+      double2 a2[2], b2[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        a2[p] = *reinterpret_cast<const double2 *>(col + ar[p]);
+        b2[p] = *reinterpret_cast<const double2 *>(col + br[p]);
+      }
+      const double af[4] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y}, bf[4] = {b2[0].x, b2[0].y, b2[1].x, b2[1].y};
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) dmma_m8n8k4(acc[rb][cb][0], acc[rb][cb][1], af[rb], bf[cb]);
+      col += 4 * (long)lda;
+    }
+    // C fragment of tile (rb = 2 p + h, cb = 2 q + g): row slot fr -> row 16 p + 2 fr + h, column slots 2 fk, 2 fk + 1 ->
+    // columns 16 q + 4 fk + g and 16 q + 4 fk + 2 + g
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int row = 16 * (rb >> 1) + 2 * fr + (rb & 1), c0 = 16 * (cb >> 1) + 4 * fk + (cb & 1);
+        acc_w[row * LD + c0] = acc[rb][cb][0];
+        acc_w[row * LD + c0 + 2] = acc[rb][cb][1];
+      }
+    return;
+  }
+#endif
   // rows beyond n read row n-1 instead (finite data, results discarded)
   int arow[4], brow[4];
 #pragma unroll

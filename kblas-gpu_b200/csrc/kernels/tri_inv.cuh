@@ -90,3 +90,84 @@ tri_inv_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int 
 }
 
 }  // namespace kblasx
+
+namespace kblasx {
+
+// ---- LAUUM for n > 32: A := L^T L (lower triangle), in place, one warp per matrix ------------------------------------------
+// Block row J of the result, J ascending, needs only block rows I >= J of L:
+//   (L^T L)[J][K] = sum_{I >= J} L[I][J]^T L[I][K],  K <= J,
+// so writing block row J (columns K < J first, the diagonal block last: every product of the row reads L[J][J]) never
+// destroys an operand of a later product.  Each 32 x 32 product is staged through shared memory (coalesced loads; the
+// triangular blocks L[J][J] are zero-filled above the diagonal) and accumulated in dot form, lane = result column.
+// The reference composes the same result recursively from LAUUM + SYRK + TRMM launches (Xlauum_batch_drivers.cuh:31-);
+// this is one launch and needs neither workspace nor the TRMM routine.
+template <typename T>
+struct LauumBlockedSmem {
+  static constexpr int NB = 32, P = 33;
+  static constexpr int per_warp = NB * NB + NB * P;  // L[I][J] in memory order, L[I][K] with an odd column pitch
+};
+
+template <typename T, int WARPS, bool STRIDED>
+__global__ void __launch_bounds__(WARPS * 32)
+lauum_blocked_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount) {
+  constexpr int NB = 32, P = LauumBlockedSmem<T>::P;
+  typedef typename Vec2T<T>::type V2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T *SJ = reinterpret_cast<T *>(smem_raw) + warp * LauumBlockedSmem<T>::per_warp;
+  T *SK = SJ + NB * NB;
+  const long mat = (long)blockIdx.x * WARPS + warp;
+  if (mat >= (long)batchCount) return;  // warp-uniform
+  T *__restrict__ A = Aref.at(mat);
+  const int nblk = (n + NB - 1) / NB;
+  for (int J = 0; J < nblk; ++J) {
+    const int j0 = J * NB, jb = (n - j0 < NB) ? (n - j0) : NB;
+    for (int K = 0; K <= J; ++K) {
+      const int k0 = K * NB, kb = (n - k0 < NB) ? (n - k0) : NB;
+      T C[NB];
+#pragma unroll
+      for (int r = 0; r < NB; ++r) C[r] = T(0);
+      for (int I = J; I < nblk; ++I) {
+        const int i0 = I * NB, ib = (n - i0 < NB) ? (n - i0) : NB;
+        __syncwarp();  // the previous product is done with the tiles
+        {
+          T vj[NB], vk[NB];
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            vj[c] = T(0);
+            vk[c] = T(0);
+            ldg_stream_if(vj[c], A + (i0 + lane) + (long)(j0 + c) * lda, lane < ib && c < jb && !(I == J && lane < c));
+            ldg_stream_if(vk[c], A + (i0 + lane) + (long)(k0 + c) * lda, lane < ib && c < kb && !(I == K && lane < c));
+          }
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            SJ[c * NB + lane] = vj[c];
+            SK[c * P + lane] = vk[c];
+          }
+        }
+        __syncwarp();
+        T v[NB];
+#pragma unroll
+        for (int t = 0; t < NB; ++t) v[t] = SK[lane * P + t];  // column `lane` of L[I][K]
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+          T acc[2] = {T(0), T(0)};
+#pragma unroll
+          for (int t = 0; t < NB; t += 2) {
+            const V2 s2 = lds_pair(SJ + r * NB + t);  // L[i0 + t][j0 + r], L[i0 + t + 1][j0 + r]
+            acc[0] = fma_t(s2.x, v[t], acc[0]);
+            acc[1] = fma_t(s2.y, v[t + 1], acc[1]);
+          }
+          C[r] += acc[0] + acc[1];
+        }
+      }
+      // column k0 + lane of block (J, K); only the lower part of the diagonal block
+#pragma unroll
+      for (int r = 0; r < NB; ++r)
+        stg_stream_if(A + (j0 + r) + (long)(k0 + lane) * lda, C[r], r < jb && lane < kb && (K < J || r >= lane));
+    }
+  }
+}
+
+}  // namespace kblasx

@@ -3,8 +3,8 @@
 // Counterparts of reference src/batch_triangular/X{trtri,lauum,potri,poti}_batch.cu and their drivers
 // (Xtrtri_batch_drivers.cuh:31-125, Xlauum_batch_drivers.cuh:31-, Xpotri_batch_drivers.cuh:31-, Xpoti_batch_drivers.cuh:31-89).
 // n <= 32: one launch of kernels/tri_inv.cuh (poti: potrf launch + potri launch).  trtri for n > 32 follows the reference's
-// own recursion over TRSM (Xtrtri_batch_drivers.cuh:31-84) on this library's one-launch TRSM; lauum / potri / poti for
-// n > 32 need the TRMM sibling, which is out of this path's scope -> KBLAS_NotImplemented.
+// own recursion over TRSM (Xtrtri_batch_drivers.cuh:31-84) on this library's one-launch TRSM; lauum for n > 32 is one
+// launch of the blocked in-place kernel (no TRMM / SYRK launches, no workspace); potri = trtri + lauum, poti = potrf + potri.
 // Contract as the reference: Lower only, NonUnit only ("(Upper | DIAG) TRTRI_BATCH is not implemented yet",
 // Xtrtri_batch_drivers.cuh:96-99), in place, info_array not written, workspace protocol honoured.
 #include "kblas.h"
@@ -69,6 +69,19 @@ static int trtri_rec(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int
   return trtri_rec<T, STRIDED>(h, n2, sub(A, n1, n1, lda), lda, batchCount);
 }
 
+// A := L^T L for n > 32 (kernels/tri_inv.cuh, lauum_blocked_kernel)
+template <typename T, bool STRIDED>
+static int lauum_blocked(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * LauumBlockedSmem<T>::per_warp * sizeof(T);
+  auto kern = lauum_blocked_kernel<T, WARPS, STRIDED>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)((batchCount + WARPS - 1) / WARPS), WARPS * 32, smem, h->stream>>>(n, A, lda, batchCount);
+  h->note_launch("lauum_blocked");
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 enum InvRoutine { R_TRTRI, R_LAUUM, R_POTRI, R_POTI };
 
 template <typename T, bool STRIDED>
@@ -90,10 +103,14 @@ static int inv_family(KBlasHandle *h, int routine, char uplo, char diag, int n, 
   else poti_batch_wsquery_core(STRIDED, n, batchCount, &need);
   if (!need.isSufficient(&h->work_space.allocated_ws_state)) return KBLAS_InsufficientWorkspace;
   if (routine == R_TRTRI) return trtri_rec<T, STRIDED>(h, n, A, lda, batchCount);
-  if (n > 32) return KBLAS_NotImplemented;  // needs the TRMM sibling (out of scope)
-  if (routine == R_LAUUM) return tri_inv_small<T, TI_LAUUM, STRIDED>(h, n, A, lda, batchCount);
   if (routine == R_POTI) check_ret_error((potrf_batch_core<T, STRIDED>(h, uplo, n, A, lda, batchCount, info)));
-  return tri_inv_small<T, TI_POTRI, STRIDED>(h, n, A, lda, batchCount);
+  if (n <= 32) {
+    if (routine == R_LAUUM) return tri_inv_small<T, TI_LAUUM, STRIDED>(h, n, A, lda, batchCount);
+    return tri_inv_small<T, TI_POTRI, STRIDED>(h, n, A, lda, batchCount);
+  }
+  // n > 32: potri = trtri (TRSM recursion) + lauum (one blocked launch), as Xpotri_batch_drivers.cuh composes it
+  if (routine != R_LAUUM) check_ret_error((trtri_rec<T, STRIDED>(h, n, A, lda, batchCount)));
+  return lauum_blocked<T, STRIDED>(h, n, A, lda, batchCount);
 }
 
 }  // namespace kblasx

@@ -1,7 +1,7 @@
 """kblas{S,D}{trtri,lauum,potri,poti}_batch[_strided]: the consumers of the Cholesky factor.
 CPU: the oracle's definitions against numpy (inverse / Gram matrix).  GPU: the CUDA path against the oracle
 (100 n eps scaled), plus the defining identities (L X = I, A A^-1 = I); strided and pointer array; n <= 32 in one launch,
-trtri for any n through the reference's TRSM recursion; the sizes that need the out-of-scope TRMM sibling answer NotImplemented."""
+trtri for any n through the reference's TRSM recursion; lauum / potri / poti for n > 32 through the blocked in-place LAUUM."""
 import numpy as np
 import pytest
 
@@ -88,28 +88,54 @@ def test_inverse_family_small_vs_oracle(env, p, which, n):
 @pytest.mark.gpu
 @pytest.mark.parametrize("p", ["D", "S"])
 @pytest.mark.parametrize("n", [33, 48, 64, 100, 128, 200, 256])
-def test_trtri_large_n_and_the_unimplemented_siblings(env, p, n):
+def test_inverse_family_large_n(env, p, n):
+    """n > 32: trtri through the TRSM recursion, lauum as one blocked in-place launch, potri = trtri + lauum, poti = potrf +
+    potri -- against the oracle and against the defining identities (L X = I, X = L^T L, X A = I)."""
     kb, h, torch = env
     dt = DT[p]
+    es = np.dtype(dt).itemsize
     eps = U.EPS[dt]
-    batch = 6
-    L0 = U.rand_spd_batch(batch, n, dtype=dt, seed=n)
+    batch, lda = 6, n + 3
+    A0 = U.rand_spd_batch(batch, n, lda=lda, dtype=dt, seed=n, extra_cols=1)
+    L0 = A0.copy()
     U.oracle_potrf(L0, n)
     h.inv_batch_wsquery("poti", n, batch)
+    h.inv_batch_wsquery("poti", n, batch, strided=False)
     h.allocate_workspace()
-    dA = torch.from_numpy(L0).cuda()
-    assert h.inv_batch_strided("trtri", "L", n, dA, n, n * n, batch, None) == kb.KBLAS_Success
-    torch.cuda.synchronize()
-    X = np.tril(U.as_mats(dA.cpu().numpy(), n, n)).astype(np.float64)
     Lm = np.tril(U.as_mats(L0, n, n)).astype(np.float64)
+    Am = U.as_mats(A0, n, n).astype(np.float64)
+    Am = np.tril(Am) + np.transpose(np.tril(Am, -1), (0, 2, 1))
     I = np.eye(n)[None]
-    assert np.abs(Lm @ X - I).max() <= 100 * n * eps * np.abs(Lm).max() * np.abs(X).max()
-    ref = L0.copy()
-    U.oracle_inv("trtri", n, ref)
-    assert np.abs(X - np.tril(U.as_mats(ref, n, n))).max() <= 100 * n * eps * max(1.0, np.abs(X).max())
-    for which in ("lauum", "potri", "poti"):
-        assert h.inv_batch_strided(which, "L", n, dA, n, n * n, batch, None) == kb.KBLAS_NotImplemented
-    h2 = kb.Handle()     # workspace protocol skipped where the reference's recursion needs pointer workspace
+    for which in ("trtri", "lauum", "potri", "poti"):
+        start = A0 if which == "poti" else L0
+        dA = torch.from_numpy(start).cuda()
+        assert h.inv_batch_strided(which, "L", n, dA, lda, (n + 1) * lda, batch, None) == kb.KBLAS_Success, which
+        torch.cuda.synchronize()
+        got = dA.cpu().numpy()
+        X = np.tril(U.as_mats(got, n, n)).astype(np.float64)
+        if which == "trtri":
+            assert np.abs(Lm @ X - I).max() <= 100 * n * eps * np.abs(Lm).max() * np.abs(X).max()
+        elif which == "lauum":
+            W = np.tril(np.transpose(Lm, (0, 2, 1)) @ Lm)
+            assert np.abs(X - W).max() <= 100 * n * eps * np.abs(W).max(), h.last_kernel
+        else:
+            Xs = X + np.transpose(np.tril(X, -1), (0, 2, 1))
+            assert np.abs(Xs @ Am - I).max() <= 1000 * n * eps * np.abs(Am).max() * np.abs(Xs).max(), (which, h.last_kernel)
+        ref = start.copy()
+        assert U.oracle_inv(which, n, ref) == 1
+        Wm = np.tril(U.as_mats(ref, n, n))
+        assert np.abs(X - Wm).max() <= 100 * n * eps * max(1.0, np.abs(Wm).max()), (which, h.last_kernel)
+        M, M0 = U.as_mats(got, n, n), U.as_mats(start, n, n)
+        assert np.array_equal(np.triu(M, 1), np.triu(M0, 1)), "strict upper triangle untouched"
+        assert np.array_equal(got[:, :, n:], start[:, :, n:]) and np.array_equal(got[:, n:, :], start[:, n:, :]), "padding untouched"
+        # pointer array, shuffled: same bits
+        dA2 = torch.from_numpy(start).cuda()
+        perm = torch.randperm(batch, device="cuda")
+        ptrs = (dA2.data_ptr() + perm * ((n + 1) * lda * es)).contiguous()
+        assert h.inv_batch(which, "L", n, ptrs, lda, batch, None, prec=p) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        assert np.array_equal(dA2.cpu().numpy(), got), which
+    h2 = kb.Handle()     # workspace protocol: the reference's recursion needs pointer workspace for the pointer-array form
     ptrs = torch.zeros(batch, dtype=torch.int64, device="cuda")
     assert h2.inv_batch("trtri", "L", n, ptrs, n, batch, None, prec=p) == kb.KBLAS_InsufficientWorkspace
     h2.destroy()
