@@ -233,13 +233,14 @@ struct PanelMmaOcc {
   static constexpr int warps_per_sm = sizeof(T) == 8 ? KX_PANEL_WARPS_PER_SM : KX_PANEL_WARPS_PER_SM_F32;
 };
 
-template <typename T, int THREADS, bool STRIDED>
-__global__ void __launch_bounds__(THREADS, (32 * PanelMmaOcc<T>::warps_per_sm) / THREADS)
-potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
-                       const int info_mode) {
+// the whole factorisation of ONE matrix by the calling CTA (THREADS threads); returns the LAPACK-style info value
+// (0, or 1 + the index of the first non-positive pivot when info_mode is set).  Also the first half of the fused POSV kernel
+// (kernels/posv_fused.cuh).
+template <typename T, int THREADS>
+__device__ __forceinline__ int potrf_panel_mma_body(const int n, T *__restrict__ A, const int lda, const int info_mode,
+                                                    unsigned char *smem_raw) {
   constexpr int NB = 32;
   constexpr int LD = PanelMmaSmem<T, THREADS>::LD;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   T *Lkk = reinterpret_cast<T *>(smem_raw);  // factored diagonal block, column-major, identity padded
   T *invd = Lkk + NB * NB;                    // 1 / diag(L_JJ)
   T *accs = invd + NB;                        // per warp: 32 x LD transpose buffer
@@ -247,7 +248,6 @@ potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, co
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  T *__restrict__ A = Aref.at(blockIdx.x);
   T *acc_w = accs + warp * NB * LD;
   int bad = 0;
 
@@ -331,7 +331,16 @@ potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, co
     __threadfence_block();
     __syncthreads();
   }
-  if (info_mode && tid == 0) info[blockIdx.x] = bad;
+  return bad;
+}
+
+template <typename T, int THREADS, bool STRIDED>
+__global__ void __launch_bounds__(THREADS, (32 * PanelMmaOcc<T>::warps_per_sm) / THREADS)
+potrf_panel_mma_kernel(const int n, BatchRef<T, STRIDED> Aref, const int lda, const int batchCount, int *__restrict__ info,
+                       const int info_mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int bad = potrf_panel_mma_body<T, THREADS>(n, Aref.at(blockIdx.x), lda, info_mode, smem_raw);
+  if (info_mode && threadIdx.x == 0) info[blockIdx.x] = bad;
 }
 
 }  // namespace kblasx

@@ -134,15 +134,15 @@ __device__ __forceinline__ void solve_update_mma(double *acc_w, const double *X,
 }
 
 // one pass (forward or backward) over all 32-column blocks.  GP = 16: matrices Aq[0], Aq[1] / Bq[0], Bq[1], lane group g owns
-// rows lane % 16 of matrix g; GP = 32: one matrix (Aq[0], Bq[0]), lane = row xr0 + lane.
-template <bool FORWARD, int GP>
+// rows lane % 16 of matrix g (MPW = 1: only matrix 0, lanes 16..31 hold no rows -- the fused POSV kernel); GP = 32: one
+// matrix (Aq[0], Bq[0]), lane = row xr0 + lane.
+template <bool FORWARD, int GP, int MPW = 32 / GP>
 __device__ __forceinline__ void tri_mma_pass(const int k, const double alpha, const double *const (&Aq)[2], const int lda,
                                              double *const (&Bq)[2], const int ldb, const int xr0, const int nrows,
                                              const bool have, double *smem_w, const int lane) {
   constexpr int NB = 32, LD = TriMmaSmem::LD, RG = TriMmaSmem::region;
-  constexpr int MPW = 32 / GP;
-  const int g = GP == 16 ? (lane >> 4) : 0;
-  const int r = GP == 16 ? (lane & 15) : lane;  // my row inside the region of my matrix
+  const int g = (GP == 16 && MPW == 2) ? (lane >> 4) : 0;
+  const int r = GP == 16 ? (lane & 15) : lane;  // my row inside the region of my matrix (MPW = 1, GP = 16: lanes 16..31 idle along)
   double *B = Bq[g];
   const int my = xr0 + r;
   const int nblk = (k + NB - 1) / NB;
