@@ -11,11 +11,12 @@
  *  - every matrix / pointer-array / info pointer is a DEVICE pointer, scalars by value;
  *  - work is enqueued on the handle's stream, asynchronously;
  *  - return value: KBLAS_Success (1) or a KBLAS_* error (<= 0), see kblas_defs.h;
- *  - only uplo = 'L' (potrf/potrs/posv/trsm), diag = 'N' (trsm) and side = 'R'
- *    (potrs/posv) are implemented, exactly as in the reference
+ *  - the reference implements only uplo = 'L' (potrf/potrs/posv/trsm), diag = 'N' (trsm) and
+ *    side = 'R' (potrs/posv) and returns KBLAS_NotImplemented for anything else
  *    (Xpotrf_batch_drivers.cuh:38-41, Xtrsm_batch_drivers.cuh:64-67,
- *     Xpotrs_batch_drivers.cuh:40-43, Xposv_batch_drivers.cuh:41-44): anything else
- *    returns KBLAS_NotImplemented;
+ *     Xpotrs_batch_drivers.cuh:40-43, Xposv_batch_drivers.cuh:41-44).  Those are the fast paths
+ *    here; uplo = 'U', diag = 'U' and side = 'L' are implemented as extensions (correct, tested, the
+ *    Upper / Unit forms not tuned); the inverse family, syrk and the packed routines stay Lower only;
  *  - info_array is NOT written by default: the reference never stores a non-SPD
  *    code (Xpotrf_batch_kernels.cuh:121-129), a non-SPD input yields NaN/Inf in the
  *    factor.  Setting env KBLAS_B200_INFO_MODE=lapack before kblasCreate() opts in

@@ -242,6 +242,7 @@ KBlasHandle::KBlasHandle(int /*use_magma*/, cudaStream_t stream_, int device_id_
   info_mode = (im && !strcmp(im, "lapack")) ? KBLASX_INFO_LAPACK : KBLASX_INFO_COMPAT;
   const char *vo = getenv("KBLAS_B200_VARIANT");
   variant_override = vo ? atoi(vo) : -1;
+  tri_flags = 0;
   const char *xs = getenv("KBLAS_B200_ELEMENT_EXACT_STORES");
   exact_stores = (xs && atoi(xs) != 0) ? 1 : 0;
   launch_count = 0;

@@ -125,6 +125,7 @@ struct KBlasHandle {
   int smem_optin_max;      // cudaDevAttrMaxSharedMemoryPerBlockOptin of device_id (227 KiB on B200)
   int info_mode;           // KBlasxInfoMode
   int variant_override;    // -1 = auto; tuning / ablation hook (env KBLAS_B200_VARIANT)
+  int tri_flags;           // TRI_FLAG_UPPER | TRI_FLAG_UNIT of the triangular solve being dispatched (0 outside such a call)
   int exact_stores;        // env KBLAS_B200_ELEMENT_EXACT_STORES=1: potrf never stores a strict-upper element
   long launch_count;       // kernels launched through this handle
   const char *last_kernel; // name of the last dispatched kernel variant

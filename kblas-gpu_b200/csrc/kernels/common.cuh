@@ -7,6 +7,12 @@ namespace kblasx {
 
 // which substitution a triangular-solve kernel runs (trsm: one of the two; potrs: both, fused)
 enum TriOp { TRI_FORWARD = 0, TRI_BACKWARD = 1, TRI_BOTH = 2 };
+// flags (the variants the reference answers KBLAS_NotImplemented for; generic kernels only):
+//   TRI_FLAG_UPPER  the factor is stored in the UPPER triangle: what is staged is L = U^T, L[r][c] = A[c + r*lda] (the caller
+//                   flips the transposition: op(U) = op'(L)); lanes then read with stride lda -- correct, not fast
+//   TRI_FLAG_UNIT   unit diagonal: the diagonal entries are not referenced, 1 / L_jj = 1
+enum { TRI_FLAG_UPPER = 1, TRI_FLAG_UNIT = 2 };
+
 
 template <typename T> struct Vec2T;
 template <> struct Vec2T<double> { typedef double2 type; };

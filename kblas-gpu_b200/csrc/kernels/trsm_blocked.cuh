@@ -29,13 +29,15 @@ __device__ __forceinline__ long b_index(int v, int e, int ldb) {
 // (zero outside nr x nc).  32 predicated loads in flight, then 32 conflict-free stores.
 template <typename T>
 __device__ __forceinline__ void stage_tile(T *Ts, const T *__restrict__ A, int lda, int r0, int c0, int nr, int nc,
-                                           int lane) {
+                                           int lane, int flags = 0) {
   constexpr int NB = 32;
   T v[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     v[i] = T(0);
-    ldg_stream_if(v[i], A + (r0 + lane) + (long)(c0 + i) * lda, lane < nr && i < nc);
+    // upper storage: L[r0 + lane][c0 + i] = U[c0 + i][r0 + lane]
+    const T *p = (flags & TRI_FLAG_UPPER) ? A + (c0 + i) + (long)(r0 + lane) * lda : A + (r0 + lane) + (long)(c0 + i) * lda;
+    ldg_stream_if(v[i], p, lane < nr && i < nc);
   }
   sched_fence();
 #pragma unroll
@@ -62,7 +64,7 @@ __device__ __forceinline__ void prefetch_tile_l2(const T *__restrict__ A, int ld
 template <typename T, bool LEFT, bool FORWARD, int GP>
 __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, const T *const (&Aq)[32 / GP], const int lda,
                                                  T *__restrict__ B, const int ldb, const int my, const bool have,
-                                                 T *Lkk_all, T *S_all, const int lane) {
+                                                 T *Lkk_all, T *S_all, const int lane, const int flags) {
   constexpr int NB = 32;
   constexpr int MPW = 32 / GP;
   constexpr int FSZ = NB * NB + NB;
@@ -109,7 +111,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       if (FORWARD) {
         // coefficient of x_K[kk] in equation c: L[j0 + c][k0 + kk] = Ts[kk*NB + c]  (axpy form)
 #pragma unroll
-        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, j0, k0, jb, kb, lane);
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, j0, k0, jb, kb, lane, flags);
 #pragma unroll 8
         for (int kk = 0; kk < NB; ++kk) {
           const T m1 = -nx[kk];
@@ -123,7 +125,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
       } else {
         // coefficient of x_K[kk] in equation c: L[k0 + kk][j0 + c] = Ts[c*NB + kk]  (dot form)
 #pragma unroll
-        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, k0, j0, kb, jb, lane);
+        for (int q = 0; q < MPW; ++q) stage_tile<T>(S_all + q * FSZ, Aq[q], lda, k0, j0, kb, jb, lane, flags);
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
           T acc[4] = {T(0), T(0), T(0), T(0)};
@@ -142,7 +144,7 @@ __device__ __forceinline__ void tri_blocked_pass(const int k, const T alpha, con
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < MPW; ++q)
-      stage_factor<T, NB>(Aq[q] + j0 + (long)j0 * lda, lda, jb, Lkk_all + q * FSZ, Lkk_all + q * FSZ + NB * NB, lane);
+      stage_factor<T, NB>(Aq[q] + j0 + (long)j0 * lda, lda, jb, Lkk_all + q * FSZ, Lkk_all + q * FSZ + NB * NB, lane, flags);
     if (FORWARD) tri_forward<T, NB>(x, Lkk, invd);
     else tri_backward<T, NB>(x, Lkk, invd);
 #pragma unroll
@@ -162,7 +164,7 @@ struct TriBlockedSmem {
 template <typename T, bool LEFT, int OP, int GP, int WARPS, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32)
 tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
-                         BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
+                         BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs, const int flags) {
   constexpr int MPW = 32 / GP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -185,9 +187,9 @@ tri_solve_blocked_kernel(const int k, const int vec, const T alpha, BatchRef<con
   T *__restrict__ B = Bref.at(mat0 + g < last ? mat0 + g : last);
 
   if (OP == TRI_FORWARD || OP == TRI_BOTH)
-    tri_blocked_pass<T, LEFT, true, GP>(k, alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane);
+    tri_blocked_pass<T, LEFT, true, GP>(k, alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane, flags);
   if (OP == TRI_BACKWARD || OP == TRI_BOTH)
-    tri_blocked_pass<T, LEFT, false, GP>(k, OP == TRI_BOTH ? T(1) : alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane);
+    tri_blocked_pass<T, LEFT, false, GP>(k, OP == TRI_BOTH ? T(1) : alpha, Aq, lda, B, ldb, my, have, Lkk_all, S_all, lane, flags);
 }
 
 }  // namespace kblasx

@@ -39,8 +39,17 @@ __device__ __forceinline__ void sched_fence() { asm volatile("bar.warp.sync 0xff
 // with the identity; invd[j] = 1 / L_jj.  One warp, coalesced column reads.  Two phases so that
 // all NP predicated loads are in flight before the first shared-memory store waits on one.
 template <typename T, int NP>
-__device__ __forceinline__ void stage_factor_load(T (&v)[NP], const T *__restrict__ A, int lda, int k, int lane) {
+__device__ __forceinline__ void stage_factor_load(T (&v)[NP], const T *__restrict__ A, int lda, int k, int lane, int flags = 0) {
   constexpr int SE = SectorElems<T>::value;
+  if (flags & TRI_FLAG_UPPER) {
+#pragma unroll
+    for (int col = 0; col < NP; ++col) {
+      const bool inside = (lane < k) && (col < k);
+      v[col] = (!inside && lane == col) ? T(1) : T(0);
+      ldg_stream_if(v[col], A + col + (long)lane * lda, inside && lane >= col);
+    }
+    return;
+  }
 #pragma unroll
   for (int col = 0; col < NP; ++col) {
     const bool inside = (lane < k) && (col < k);
@@ -49,7 +58,8 @@ __device__ __forceinline__ void stage_factor_load(T (&v)[NP], const T *__restric
   }
 }
 template <typename T, int NP>
-__device__ __forceinline__ void stage_factor_store(const T (&v)[NP], T *__restrict__ Ls, T *__restrict__ invd, int lane) {
+__device__ __forceinline__ void stage_factor_store(const T (&v)[NP], T *__restrict__ Ls, T *__restrict__ invd, int lane,
+                                                   int flags = 0) {
   // every load of the batch is issued before the first store can wait on one (ptxas otherwise
   // interleaves LDG / STS to save registers and the in-order warp eats one memory latency per column)
   sched_fence();
@@ -60,15 +70,15 @@ __device__ __forceinline__ void stage_factor_store(const T (&v)[NP], T *__restri
     if (lane < NP) Ls[lane + col * NP] = v[col];
     dg = (lane == col) ? v[col] : dg;
   }
-  if (lane < NP) invd[lane] = T(1) / dg;
+  if (lane < NP) invd[lane] = (flags & TRI_FLAG_UNIT) ? T(1) : T(1) / dg;
   __syncwarp();
 }
 template <typename T, int NP>
 __device__ __forceinline__ void stage_factor(const T *__restrict__ A, int lda, int k, T *__restrict__ Ls,
-                                             T *__restrict__ invd, int lane) {
+                                             T *__restrict__ invd, int lane, int flags = 0) {
   T v[NP];
-  stage_factor_load<T, NP>(v, A, lda, k, lane);
-  stage_factor_store<T, NP>(v, Ls, invd, lane);
+  stage_factor_load<T, NP>(v, A, lda, k, lane, flags);
+  stage_factor_store<T, NP>(v, Ls, invd, lane, flags);
 }
 
 // Column j of the staged factor, rows > j, as NP/2 register pairs (pair p = rows 2p, 2p+1).
@@ -152,7 +162,7 @@ struct TriSmem {
 template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32, 3)
 tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
-                       BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs) {
+                       BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int slabs, const int flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -169,8 +179,8 @@ tri_solve_small_kernel(const int k, const int vec, const T alpha, BatchRef<const
   const T *__restrict__ A = Aref.at(mat);
   T *__restrict__ B = Bref.at(mat);
   T fv[NP];
-  stage_factor_load<T, NP>(fv, A, lda, k, lane);  // NP predicated loads in flight
-  stage_factor_store<T, NP>(fv, Ls, invd, lane);
+  stage_factor_load<T, NP>(fv, A, lda, k, lane, flags);  // NP predicated loads in flight
+  stage_factor_store<T, NP>(fv, Ls, invd, lane, flags);
 
   T x[NP];
   const int my = v0 + lane;  // my vector

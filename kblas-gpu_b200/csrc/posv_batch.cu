@@ -14,10 +14,7 @@ namespace kblasx {
 template <typename T, bool STRIDED>
 static int posv_batch_core(KBlasHandle *h, char side, char uplo, int m, int n, BatchRef<T, STRIDED> A, int lda,
                            BatchRef<T, STRIDED> B, int ldb, int batchCount, int *info) {
-  if (uplo == KBLAS_Upper) {
-    printf("(Left | Upper) POSV_BATCH is not implemented yet\n");  // reference drivers.cuh:42
-    return KBLAS_NotImplemented;
-  }
+  // uplo = Upper is KBLAS_NotImplemented in the reference (drivers.cuh:41-44); potrf and potrs implement it here
   // side L (A of order m, A X = B) is an extension: the reference returns KBLAS_NotImplemented (drivers.cuh:41-44)
   if (side != KBLAS_Left && side != KBLAS_Right) return KBLAS_NotImplemented;
   check_ret_error((potrf_batch_core<T, STRIDED>(h, uplo, side == KBLAS_Left ? m : n, A, lda, batchCount, info)));

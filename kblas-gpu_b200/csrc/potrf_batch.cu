@@ -9,6 +9,7 @@
 #include "kernels/potrf_small.cuh"
 #include "kernels/potrf_panel_mma.cuh"
 #include "kernels/potrf_smem.cuh"
+#include "kernels/tri_swap.cuh"
 #include "potrf_batch.h"
 
 namespace kblasx {
@@ -117,12 +118,35 @@ static int potrf_panel_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
                                                 batchCount, info);
 }
 
+// A := A^T on the n x n leading blocks (kernels/tri_swap.cuh)
+template <typename T, bool STRIDED>
+static int transpose_inplace(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, int lda, int batchCount) {
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * TriSwapSmem<T>::per_warp * sizeof(T);
+  auto kern = transpose_inplace_kernel<T, WARPS, STRIDED>;
+  check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
+  kern<<<(unsigned)((batchCount + WARPS - 1) / WARPS), WARPS * 32, smem, h->stream>>>(n, A, lda, batchCount);
+  h->note_launch("transpose_inplace");
+  check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
+  return KBLAS_Success;
+}
+
 // Xpotrf_batch_core of the reference (Xpotrf_batch_drivers.cuh:30-137)
 template <typename T, bool STRIDED>
 int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, int lda, int batchCount, int *info) {
   if (uplo == KBLAS_Upper) {
-    printf("Upper POTRF_BATCH is not implemented yet\n");  // same line as the reference prints (:39)
-    return KBLAS_NotImplemented;
+    // KBLAS_NotImplemented in the reference (:38-41).  Extension: A = U^T U through the lower kernels on
+    // the transposed matrix -- transpose, factor, transpose back; the strictly lower triangle keeps its contents.
+    if (batchCount <= 0) {
+      check_error_ret(cudaErrorInvalidConfiguration, KBLAS_UnknownError);
+    }
+    if (n <= 0) return KBLAS_Success;
+    check_ret_error((transpose_inplace<T, STRIDED>(h, n, A, lda, batchCount)));
+    check_ret_error((potrf_batch_core<T, STRIDED>(h, KBLAS_Lower, n, A, lda, batchCount, info)));
+    const char *factor_kernel = h->last_kernel;
+    check_ret_error((transpose_inplace<T, STRIDED>(h, n, A, lda, batchCount)));
+    h->last_kernel = factor_kernel;
+    return KBLAS_Success;
   }
   if (batchCount <= 0) {
     // reference: grid.x == 0 -> launch error -> KBLAS_UnknownError (drivers.cuh:82-88)

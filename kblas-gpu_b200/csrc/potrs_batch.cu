@@ -13,10 +13,8 @@ namespace kblasx {
 template <typename T, bool STRIDED>
 int potrs_batch_core(KBlasHandle *h, char side, char uplo, int m, int n, BatchRef<const T, STRIDED> A, int lda,
                      BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  if (uplo == KBLAS_Upper) {
-    printf("(Left | Upper) POTRS_BATCH is not implemented yet\n");  // reference drivers.cuh:41
-    return KBLAS_NotImplemented;
-  }
+  // uplo = Upper (A = U^T U) is KBLAS_NotImplemented in the reference (drivers.cuh:40-43); here L = U^T is staged by the
+  // generic solve kernels (extension)
   // side L -- A X = B, A = L L^T of order m, B is m x n -- is KBLAS_NotImplemented in the reference (drivers.cuh:40-43);
   // here it is the same fused forward + backward substitution with the factor acting from the left (SURVEY.md §8(f)3,
   // documented extension): L Y = B, L^T X = Y.
@@ -26,7 +24,10 @@ int potrs_batch_core(KBlasHandle *h, char side, char uplo, int m, int n, BatchRe
   // which answers KBLAS_NotImplemented (drivers.cuh:85-98, Xtrsm_batch_drivers.cuh:267-270).
   // A 1 x 1 factor is a perfectly good problem: solved here (documented deviation).
   if ((left ? m : n) <= 0) return KBLAS_NotImplemented;
-  return tri_solve_core<T, STRIDED>(h, left, TRI_BOTH, m, n, T(1), A, lda, B, ldb, batchCount);
+  h->tri_flags = (uplo == KBLAS_Upper) ? TRI_FLAG_UPPER : 0;
+  const int rc = tri_solve_core<T, STRIDED>(h, left, TRI_BOTH, m, n, T(1), A, lda, B, ldb, batchCount);
+  h->tri_flags = 0;
+  return rc;
 }
 
 #define KX_INST(T, S)                                                                                      \

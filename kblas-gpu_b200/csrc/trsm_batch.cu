@@ -46,18 +46,20 @@ KX_INST(double, false)
 template <typename T, bool STRIDED>
 static int trsm_batch_core(KBlasHandle *h, char side, char uplo, char trans, char diag, int m, int n, T alpha,
                            BatchRef<const T, STRIDED> A, int lda, BatchRef<T, STRIDED> B, int ldb, int batchCount) {
-  if (uplo == KBLAS_Upper || diag == KBLAS_Unit) {
-    printf("(Upper | Unit) TRSM_BATCH is not implemented yet\n");  // reference drivers.cuh:65
-    return KBLAS_NotImplemented;
-  }
+  // Upper and Unit are KBLAS_NotImplemented in the reference (Xtrsm_batch_drivers.cuh:64-67); here they are served by the
+  // generic kernels (documented extension): an upper factor U is staged as L = U^T, so op(U) = op'(L)
+  const bool upper = (uplo == KBLAS_Upper), unit = (diag == KBLAS_Unit);
   const bool left = (side == KBLAS_Left);
   if (!left && side != KBLAS_Right) return KBLAS_NotImplemented;
   // the reference falls through to "should not reach this" when the triangular dimension is 0
   if ((left ? m : n) <= 0) return KBLAS_NotImplemented;  // drivers.cuh:267-270
-  const bool notrans = (trans == KBLAS_NoTrans);
+  const bool notrans = (trans == KBLAS_NoTrans) != upper;
   // forward: (R, T) and (L, N); backward: (R, N) and (L, T)
   const int op = (left == notrans) ? TRI_FORWARD : TRI_BACKWARD;
-  return tri_solve_core<T, STRIDED>(h, left, op, m, n, alpha, A, lda, B, ldb, batchCount);
+  h->tri_flags = (upper ? TRI_FLAG_UPPER : 0) | (unit ? TRI_FLAG_UNIT : 0);
+  const int rc = tri_solve_core<T, STRIDED>(h, left, op, m, n, alpha, A, lda, B, ldb, batchCount);
+  h->tri_flags = 0;
+  return rc;
 }
 
 static int trsm_ws_check(KBlasHandle *h, bool strided, char side, int m, int n, int batchCount) {

@@ -25,7 +25,7 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
   const size_t smem = (size_t)WARPS * TriSmem<NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_small_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
-  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs, h->tri_flags);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -149,7 +149,7 @@ static int launch_tri_blocked_gp(KBlasHandle *h, const char *name, int k, int ve
   auto kern = tri_solve_blocked_kernel<T, LEFT, OP, GP, WARPS, STRIDED>;
   const size_t smem = per_warp * WARPS;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
-  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, slabs, h->tri_flags);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -176,8 +176,8 @@ template <typename T, bool LEFT, int OP, bool STRIDED>
 static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                               BatchRef<T, STRIDED> B, int ldb, int batchCount) {
   if constexpr (sizeof(T) == 8 && !LEFT) {
-    // variant 44 keeps the FMA kernels (A/B)
-    if (h->variant_override != 44 && vec > 8) {
+    // variant 44 keeps the FMA kernels (A/B); Upper / Unit factors are staged by the generic kernels only
+    if (h->variant_override != 44 && vec > 8 && h->tri_flags == 0) {
       if (vec <= 16) return launch_tri_mma<OP, 16, STRIDED>(h, "tri_mma<GP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
       return launch_tri_mma<OP, 32, STRIDED>(h, "tri_mma<GP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
     }
@@ -192,6 +192,12 @@ static int launch_tri_blocked(KBlasHandle *h, int k, int vec, T alpha, BatchRef<
 template <typename T, bool LEFT, int OP, bool STRIDED>
 static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                         BatchRef<T, STRIDED> B, int ldb, int batchCount) {
+  if (h->tri_flags != 0) {  // Upper storage / unit diagonal: only the generic kernel stages those (kernels/trsm_small.cuh)
+    if (k <= 8) return launch_tri_small<T, 8, LEFT, OP, STRIDED>(h, "tri_small<NP=8>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 16) return launch_tri_small<T, 16, LEFT, OP, STRIDED>(h, "tri_small<NP=16>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    if (k <= 24) return launch_tri_small<T, 24, LEFT, OP, STRIDED>(h, "tri_small<NP=24>", k, vec, alpha, A, lda, B, ldb, batchCount);
+    return launch_tri_small<T, 32, LEFT, OP, STRIDED>(h, "tri_small<NP=32>", k, vec, alpha, A, lda, B, ldb, batchCount);
+  }
   // measured (B200, 2^20 problems, side L): dual vs one-vector kernel  fp64 k=32 4.7-5.1 vs 5.1-5.4 ms, k=24 3.0-3.4 vs
   // 3.6-3.9; fp32 k=24 2.07 vs 2.35 but k=32 2.96-3.07 vs 2.77-2.83 -> fp32 k=32 side L stays on the older kernel
   if constexpr (LEFT) {

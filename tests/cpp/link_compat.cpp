@@ -129,8 +129,8 @@ static int run(const char *tag) {
   std::vector<int> hi(batch);
   cudaMemcpy(hi.data(), info, sizeof(int) * batch, cudaMemcpyDeviceToHost);
   for (int v : hi) bad += (v != 5);
-  bad += kblas_potrf_batch(h, 'U', n, dA, lda, sA, batch, info) != KBLAS_NotImplemented;
-  bad += kblas_potrs_batch(h, 'R', 'U', m, n, (const T *)dA, lda, sA, dB, ldb, sB, batch) != KBLAS_NotImplemented;
+  bad += kblas_trsm_batch(h, 'X', 'L', 'N', 'N', m, n, (T)1, (const T *)dA, lda, sA, dB, ldb, sB, batch) != KBLAS_NotImplemented;
+  bad += kblas_potrs_batch(h, 'X', 'L', m, n, (const T *)dA, lda, sA, dB, ldb, sB, batch) != KBLAS_NotImplemented;
   OK(kblasFreeWorkspace(h));
   OK(kblasDestroy(&h));
   cudaFree(dA); cudaFree(dB); cudaFree(dA2); cudaFree(dB2); cudaFree(pA); cudaFree(pB); cudaFree(info);

@@ -175,8 +175,8 @@ def test_potrf_return_codes(env):
     n, batch = 16, 4
     dA = _dev(torch, U.rand_spd_batch(batch, n))
     before = dA.clone()
-    assert h.potrf_batch_strided("U", n, dA, n, n * n, batch, None) == kb.KBLAS_NotImplemented
     assert h.potrf_batch_strided("L", n, dA, n, n * n, 0, None) == kb.KBLAS_UnknownError  # empty grid in the reference
+    assert h.potrf_batch_strided("U", n, dA, n, n * n, 0, None) == kb.KBLAS_UnknownError
     assert h.potrf_batch_strided("L", 0, dA, n, n * n, batch, None) == kb.KBLAS_Success
     torch.cuda.synchronize()
     assert torch.equal(dA, before)
@@ -441,6 +441,102 @@ def test_right_side_one_vector_kernel(env, k, vec, pad):
     assert np.abs(dB.cpu().numpy()[:, :, :vec] - Bo[:, :, :vec]).max() <= tol
 
 
+def _tri_batch(batch, k, lda, dt, upper, seed):
+    """well-conditioned triangular matrices (batch, k, lda) column-major: diagonal in [1, 2), off-diagonal 0.2 * U(-1, 1) in the
+    stored triangle, NaN in the other triangle and in the padding (they must never be referenced)"""
+    rng = np.random.default_rng(seed)
+    M = 0.2 * (2 * rng.random((batch, k, k)) - 1)
+    M = np.triu(M, 1) if upper else np.tril(M, -1)               # [b, row, col]
+    M = M + np.eye(k)[None] * (1 + rng.random((batch, k, 1)))
+    A = np.full((batch, k, lda), np.nan, dtype=dt)
+    keep = np.triu(np.ones((k, k), bool)) if upper else np.tril(np.ones((k, k), bool))
+    cm = np.transpose(M, (0, 2, 1)).astype(dt)                    # [b, col, row]
+    A[:, :, :k] = np.where(np.transpose(keep)[None], cm, np.nan)
+    return A, M.astype(dt).astype(np.float64)
+
+
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("k,other", [(5, 7), (16, 16), (32, 32), (24, 40), (40, 16), (100, 9), (64, 33)])
+def test_upper_and_unit_extensions(env, p, k, other):
+    """uplo = Upper and diag = Unit are KBLAS_NotImplemented in the reference (Xtrsm_batch_drivers.cuh:64-67,
+    Xpotrf_batch_drivers.cuh:38-41, Xpotrs_batch_drivers.cuh:40-43) and implemented here: all 16 trsm
+    variants against a float64 numpy solve, with NaN in the triangle (and, for Unit, on the diagonal) that must not be
+    referenced; potrf Upper bit-identical to the transposed Lower factor; potrs / posv Upper against the Lower solution."""
+    kb, h, torch = env
+    dt = DT[p]
+    eps = U.EPS[dt]
+    batch, alpha = 19, 0.28
+    lda = k + 1
+    h.posv_batch_strided_wsquery("R", max(k, other), max(k, other), batch)
+    h.posv_batch_strided_wsquery("L", max(k, other), max(k, other), batch)
+    h.allocate_workspace()
+    for uplo in ("U", "L"):
+        A, M = _tri_batch(batch, k, lda, dt, uplo == "U", seed=k + (uplo == "U"))
+        for diag in ("N", "U"):
+            if uplo == "L" and diag == "N":
+                continue  # the reference's own case: covered everywhere else
+            Ad, Md = A.copy(), M.copy()
+            if diag == "U":
+                Ad[:, np.arange(k), np.arange(k)] = np.nan
+                Md[:, np.arange(k), np.arange(k)] = 1.0
+            dA = _dev(torch, Ad)
+            for side in ("L", "R"):
+                m, n = (k, other) if side == "L" else (other, k)
+                B0 = U.rand_batch(batch, m, n, ld=m + 2, dtype=dt, seed=m * 100 + n)
+                Bm = U.as_mats(B0, m, n).astype(np.float64)
+                for trans in ("N", "T"):
+                    Op = Md if trans == "N" else np.transpose(Md, (0, 2, 1))
+                    want = np.linalg.solve(Op, alpha * Bm) if side == "L" else np.transpose(
+                        np.linalg.solve(np.transpose(Op, (0, 2, 1)), np.transpose(alpha * Bm, (0, 2, 1))), (0, 2, 1))
+                    dB = _dev(torch, B0)
+                    rc = h.trsm_batch_strided(side, uplo, trans, diag, m, n, alpha, dA, lda, k * lda, dB, m + 2, n * (m + 2), batch)
+                    torch.cuda.synchronize()
+                    assert rc == kb.KBLAS_Success
+                    got = dB.cpu().numpy()
+                    X = U.as_mats(got, m, n).astype(np.float64)
+                    assert np.isfinite(X).all(), (uplo, diag, side, trans, h.last_kernel)
+                    assert np.abs(X - want).max() <= 100 * k * eps * max(1.0, np.abs(want).max()), (uplo, diag, side, trans, h.last_kernel)
+                    assert np.array_equal(got[:, :, m:], B0[:, :, m:]), "ldb padding untouched"
+            assert np.array_equal(dA.cpu().numpy(), Ad, equal_nan=True), "A is read-only"
+    # ---- potrf / potrs / posv with uplo = Upper --------------------------------------------------------------------
+    A0 = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=k + 3)
+    sym = U.as_mats(A0, k, k)
+    sym = np.tril(sym) + np.transpose(np.tril(sym, -1), (0, 2, 1))
+    Afull = A0.copy()
+    Afull[:, :, :k] = np.transpose(sym, (0, 2, 1))       # both triangles stored
+    dL, dU = _dev(torch, Afull), _dev(torch, Afull)
+    assert h.potrf_batch_strided("L", k, dL, lda, k * lda, batch, None) == kb.KBLAS_Success
+    assert h.potrf_batch_strided("U", k, dU, lda, k * lda, batch, None) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    Lm, Um = U.as_mats(dL.cpu().numpy(), k, k), U.as_mats(dU.cpu().numpy(), k, k)
+    assert np.array_equal(np.triu(Um), np.transpose(np.tril(Lm), (0, 2, 1))), "U = L^T, bit for bit"
+    assert np.array_equal(np.tril(Um, -1), np.tril(sym, -1)), "strictly lower triangle untouched"
+    assert np.array_equal(dU.cpu().numpy()[:, :, k:], Afull[:, :, k:]), "padding untouched"
+    for side in ("R", "L"):
+        m, n = (other, k) if side == "R" else (k, other)
+        B0 = U.rand_batch(batch, m, n, ld=m + 1, dtype=dt, seed=7 * m + n)
+        dB1, dB2, dB3 = _dev(torch, B0), _dev(torch, B0), _dev(torch, B0)
+        assert h.potrs_batch_strided(side, "L", m, n, dL, lda, k * lda, dB1, m + 1, n * (m + 1), batch) == kb.KBLAS_Success
+        assert h.potrs_batch_strided(side, "U", m, n, dU, lda, k * lda, dB2, m + 1, n * (m + 1), batch) == kb.KBLAS_Success
+        dA3 = _dev(torch, Afull)
+        assert h.posv_batch_strided(side, "U", m, n, dA3, lda, k * lda, dB3, m + 1, n * (m + 1), batch, None) == kb.KBLAS_Success
+        torch.cuda.synchronize()
+        X1, X2, X3 = (U.as_mats(d.cpu().numpy(), m, n).astype(np.float64) for d in (dB1, dB2, dB3))
+        tol = 100 * k * eps * max(1.0, np.abs(X1).max())
+        assert np.abs(X2 - X1).max() <= tol and np.abs(X3 - X1).max() <= tol, (side, h.last_kernel)
+        assert torch.equal(dA3, dU), "posv Upper leaves the same factor as potrf Upper"
+    # pointer-array form of the Upper factorisation: same bits
+    es = np.dtype(dt).itemsize
+    dP = _dev(torch, Afull)
+    perm = torch.randperm(batch, device="cuda")
+    ptrs = (dP.data_ptr() + perm * (k * lda * es)).contiguous()
+    h.potrf_batch_wsquery(k, batch)
+    h.allocate_workspace()
+    assert h.potrf_batch("U", k, ptrs, lda, batch, None, prec=p) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert torch.equal(dP, dU)
+
+
 def _slack_copy(torch, a, off):
     """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
     `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""
@@ -640,13 +736,11 @@ def test_trsm_potrs_posv_return_codes(env):
     kb, h, torch = env
     dA, dB = _dev(torch, U.rand_spd_batch(2, 8)), _dev(torch, U.rand_batch(2, 8, 8))
     a = (dA, 8, 64, dB, 8, 64, 2)
-    assert h.trsm_batch_strided("L", "U", "N", "N", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
-    assert h.trsm_batch_strided("L", "L", "N", "U", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
+    assert h.trsm_batch_strided("X", "L", "N", "N", 8, 8, 1.0, *a) == kb.KBLAS_NotImplemented
     assert h.potrs_batch_strided("X", "L", 8, 8, *a) == kb.KBLAS_NotImplemented
-    assert h.potrs_batch_strided("R", "U", 8, 8, *a) == kb.KBLAS_NotImplemented
-    assert h.posv_batch_strided("R", "U", 8, 8, *a, None) == kb.KBLAS_NotImplemented
-    # side L is an extension here (the reference: KBLAS_NotImplemented, golden posv_?_left rc = -2): see
-    # test_potrs_posv_left_side_extension
+    assert h.posv_batch_strided("X", "L", 8, 8, *a, None) == kb.KBLAS_NotImplemented
+    # side L, uplo U and diag U are extensions here (the reference: KBLAS_NotImplemented, golden posv_?_left rc = -2): see
+    # test_potrs_posv_left_side_extension and test_upper_and_unit_extensions
 
 
 @pytest.mark.parametrize("p", ["D", "S"])
