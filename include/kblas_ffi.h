@@ -158,4 +158,15 @@ int kblasxSpptrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, cons
 int kblasxDpptrf_batch_strided_host(kblasHandle_t handle, char uplo, int n, const double *AP_in, double *AP_out,
                                     long strideAP, int batchCount, int *info_host);
 
+/* (6) non-uniform TRSM: per-matrix sizes in DEVICE arrays m[b], n[b], lda[b], ldb[b]; A_array / B_array device pointer
+ *     arrays.  C twin of the reference's C++-only kblas_trsm_batch(handle, side, uplo, trans, diag, int *m, int *n, max_m,
+ *     max_n, alpha, T **A, int *lda, T **B, int *ldb, batchCount) (MAGMA builds only there, native here; all side / uplo /
+ *     trans / diag variants; matrices with a non-positive dimension are skipped) */
+int kblasxStrsm_batch_nonuniform(kblasHandle_t handle, char side, char uplo, char trans, char diag, const int *m,
+                                 const int *n, float alpha, const float *const *A_array, const int *lda,
+                                 float *const *B_array, const int *ldb, int batchCount);
+int kblasxDtrsm_batch_nonuniform(kblasHandle_t handle, char side, char uplo, char trans, char diag, const int *m,
+                                 const int *n, double alpha, const double *const *A_array, const int *lda,
+                                 double *const *B_array, const int *ldb, int batchCount);
+
 #endif /* KBLAS_B200_FFI_H */

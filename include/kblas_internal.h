@@ -85,7 +85,17 @@ int iset_value_5(int *output_array1, int input1, int *output_array2, int input2,
                   T **B, int B_row_off, int B_col_off, int ldb, long strideB, int batchCount);                 \
   int Xtrsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, int m, int n, T alpha,    \
                   T *A, int A_row_off, int A_col_off, int lda, long strideA,                                   \
-                  T *B, int B_row_off, int B_col_off, int ldb, long strideB, int batchCount);
+                  T *B, int B_row_off, int B_col_off, int ldb, long strideB, int batchCount);                  \
+  /* non-uniform batch: m, n, lda, ldb are DEVICE arrays of batchCount entries (the reference: MAGMA builds only,      \
+     Xtrsm_batch_drivers.cuh:277-367; native here, max_m / max_n / strides accepted and ignored) */                      \
+  int Xtrsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, int *m, int *n, int max_m,   \
+                  int max_n, T alpha, T **A, int A_row_off, int A_col_off, int *lda, long strideA,                \
+                  T **B, int B_row_off, int B_col_off, int *ldb, long strideB, int batchCount);                   \
+  int Xtrsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, int *m, int *n, T alpha,     \
+                  T **A, int A_row_off, int A_col_off, int *lda, long strideA,                                    \
+                  T **B, int B_row_off, int B_col_off, int *ldb, long strideB, int batchCount);                   \
+  int kblas_trsm_batch(kblasHandle_t handle, char side, char uplo, char trans, char diag, int *m, int *n,         \
+                       int max_m, int max_n, T alpha, T **A, int *lda, T **B, int *ldb, int batchCount);
 
 KBLAS_B200_DECL_INTERNAL(float)
 KBLAS_B200_DECL_INTERNAL(double)

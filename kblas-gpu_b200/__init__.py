@@ -316,6 +316,15 @@ class Handle:
         return f(self._h, _ch(side), _ch(uplo), _ch(trans), _ch(diag), m, n, alpha, _ptr(A), lda, strideA, _ptr(B),
                  ldb, strideB, batch)
 
+    def trsm_batch_nonuniform(self, side, uplo, trans, diag, m, n, alpha, A_ptrs, lda, B_ptrs, ldb, batch, prec):
+        """per-matrix sizes: m, n, lda, ldb are int32 DEVICE tensors, A_ptrs / B_ptrs int64 device tensors of addresses"""
+        f = getattr(_lib, f"kblasx{prec}trsm_batch_nonuniform")
+        f.argtypes = [C.c_void_p, C.c_char, C.c_char, C.c_char, C.c_char, C.c_void_p, C.c_void_p,
+                      C.c_double if prec == "D" else C.c_float] + [C.c_void_p] * 4 + [C.c_int]
+        f.restype = C.c_int
+        return f(self._h, _ch(side), _ch(uplo), _ch(trans), _ch(diag), _ptr(m), _ptr(n), alpha, _ptr(A_ptrs), _ptr(lda),
+                 _ptr(B_ptrs), _ptr(ldb), batch)
+
     def potrs_batch_strided(self, side, uplo, m, n, A, lda, strideA, B, ldb, strideB, batch, prec=None):
         f = getattr(_lib, f"kblas{_prec(B, prec)}potrs_batch_strided")
         return f(self._h, _ch(side), _ch(uplo), m, n, _ptr(A), lda, strideA, _ptr(B), ldb, strideB, batch)

@@ -135,29 +135,7 @@ int trsm_batch_ptrs(KBlasHandle *h, char side, char uplo, char trans, char diag,
 KX_TRSM_OFFSET_API(float)
 KX_TRSM_OFFSET_API(double)
 
-// Non-uniform batches (per-matrix m, n, lda, ldb arrays): the reference implements them ONLY through MAGMA
-// (Xtrsm_batch_nonuniform_core, Xtrsm_batch_drivers.cuh:277-367) and answers KBLAS_WrongConfig with this message
-// when built or run without it (:355-364) -- which is what a MAGMA-less build of the reference does, and what
-// these exports do.  They exist because the reference's test_Xtrsm_batch.cpp:317 links against them.
-static int trsm_nonuniform_unavailable(const char *func) {
-  printf("Configuration error at %s in file %s at line %d, MAGMA required but not enabled!\n", func, __FILE__, __LINE__);
-  return KBLAS_WrongConfig;
-}
-#define KX_TRSM_NONUNIFORM_API(T)                                                                               \
-  int Xtrsm_batch(kblasHandle_t, char, char, char, char, int *, int *, int, int, T, T **, int, int, int *, long, \
-                  T **, int, int, int *, long, int) {                                                           \
-    return trsm_nonuniform_unavailable("Xtrsm_batch_nonuniform_core");                                          \
-  }                                                                                                             \
-  int Xtrsm_batch(kblasHandle_t, char, char, char, char, int *, int *, T, T **, int, int, int *, long, T **,    \
-                  int, int, int *, long, int) {                                                                 \
-    return trsm_nonuniform_unavailable("Xtrsm_batch_nonuniform_core");                                          \
-  }                                                                                                             \
-  int kblas_trsm_batch(kblasHandle_t, char, char, char, char, int *, int *, int, int, T, T **, int *, T **,     \
-                       int *, int) {                                                                            \
-    return trsm_nonuniform_unavailable("Xtrsm_batch_nonuniform_core");                                          \
-  }
-KX_TRSM_NONUNIFORM_API(float)
-KX_TRSM_NONUNIFORM_API(double)
+// Non-uniform batches (per-matrix m, n, lda, ldb arrays): trsm_nonuniform.cu
 
 KX_TRSM_API(S, float)
 KX_TRSM_API(D, double)

@@ -537,6 +537,71 @@ def test_upper_and_unit_extensions(env, p, k, other):
     assert torch.equal(dP, dU)
 
 
+@pytest.mark.parametrize("p", ["D", "S"])
+@pytest.mark.parametrize("side,uplo,trans,diag", [("L", "L", "N", "N"), ("L", "L", "T", "N"), ("R", "L", "N", "N"), ("R", "L", "T", "N"),
+                                                   ("L", "U", "N", "U"), ("R", "U", "T", "N")])
+def test_trsm_nonuniform_batch(env, p, side, uplo, trans, diag):
+    """kblas_trsm_batch with per-matrix m[b], n[b], lda[b], ldb[b] (device arrays): MAGMA-only in the reference
+    (Xtrsm_batch_drivers.cuh:277-367), native here.  Random sizes 0..70 per matrix, every matrix
+    checked against a float64 numpy solve; storage around each matrix must stay untouched."""
+    kb, h, torch = env
+    dt = DT[p]
+    eps = U.EPS[dt]
+    rng = np.random.default_rng(11)
+    batch, alpha = 37, 0.28
+    ms = rng.integers(0, 71, batch).astype(np.int32)
+    ns = rng.integers(0, 71, batch).astype(np.int32)
+    ms[0], ns[0] = 64, 33
+    ms[1], ns[1] = 1, 1
+    ks = ms if side == "L" else ns
+    ldas = (np.maximum(ks, 1) + rng.integers(0, 3, batch)).astype(np.int32)
+    ldbs = (np.maximum(ms, 1) + rng.integers(0, 3, batch)).astype(np.int32)
+    a_off = np.concatenate([[0], np.cumsum(ldas.astype(np.int64) * np.maximum(ks, 1) + 5)])
+    b_off = np.concatenate([[0], np.cumsum(ldbs.astype(np.int64) * np.maximum(ns, 1) + 5)])
+    Abuf = np.full(a_off[-1], np.nan, dtype=dt)
+    Bbuf = np.full(b_off[-1], -3.5, dtype=dt)
+    mats, rhs = [], []
+    for b in range(batch):
+        k, m, n = int(ks[b]), int(ms[b]), int(ns[b])
+        if k > 0:
+            Ab, M = _tri_batch(1, k, int(ldas[b]), dt, uplo == "U", seed=100 + b)
+            if diag == "U":
+                Ab[0, np.arange(k), np.arange(k)] = np.nan
+                M[0, np.arange(k), np.arange(k)] = 1.0
+            Abuf[a_off[b]:a_off[b] + k * ldas[b]] = Ab.flatten()
+            mats.append(M[0])
+        else:
+            mats.append(None)
+        Bb = rng.random((max(n, 0), int(ldbs[b]))).astype(dt)
+        Bb[:, m:] = -3.5
+        Bbuf[b_off[b]:b_off[b] + n * ldbs[b]] = Bb.flatten()
+        rhs.append(Bb[:, :m].T.astype(np.float64).copy())
+    dA, dB = torch.from_numpy(Abuf).cuda(), torch.from_numpy(Bbuf).cuda()
+    es = np.dtype(dt).itemsize
+    pa = torch.from_numpy(dA.data_ptr() + a_off[:-1] * es).cuda()
+    pb = torch.from_numpy(dB.data_ptr() + b_off[:-1] * es).cuda()
+    dm, dn = torch.from_numpy(ms).cuda(), torch.from_numpy(ns).cuda()
+    dlda, dldb = torch.from_numpy(ldas).cuda(), torch.from_numpy(ldbs).cuda()
+    rc = h.trsm_batch_nonuniform(side, uplo, trans, diag, dm, dn, alpha, pa, dlda, pb, dldb, batch, p)
+    torch.cuda.synchronize()
+    assert rc == kb.KBLAS_Success
+    assert h.last_kernel == "tri_nonuniform"
+    got = dB.cpu().numpy()
+    assert np.array_equal(dA.cpu().numpy(), Abuf, equal_nan=True), "A is read-only"
+    for b in range(batch):
+        k, m, n = int(ks[b]), int(ms[b]), int(ns[b])
+        blk = got[b_off[b]:b_off[b] + n * ldbs[b]].reshape(n, ldbs[b]) if n > 0 else np.zeros((0, ldbs[b]), dt)
+        assert (got[b_off[b] + n * ldbs[b]:b_off[b + 1]] == -3.5).all(), "gap after the matrix untouched"
+        if n > 0:
+            assert (blk[:, m:] == -3.5).all(), "ldb padding untouched"
+        if m <= 0 or n <= 0:
+            continue
+        X = blk[:, :m].T.astype(np.float64)
+        Op = mats[b] if trans == "N" else mats[b].T
+        want = np.linalg.solve(Op, alpha * rhs[b]) if side == "L" else np.linalg.solve(Op.T, alpha * rhs[b].T).T
+        assert np.abs(X - want).max() <= 100 * max(k, 1) * eps * max(1.0, np.abs(want).max()), (b, m, n)
+
+
 def _slack_copy(torch, a, off):
     """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
     `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""
