@@ -18,11 +18,16 @@ WANT = [
     ("spotrf n=32 strided", r"potrf_reg_kernel<float, 32, 8, 8, 2, true, true, true>"),
     ("dpotrf n=8 strided", r"potrf_reg_kernel<double, 8, 8, 4, 4, true, true, false>"),
     ("dpotrs / dtrsm k=32 strided, side R fused fwd+bwd", r"tri_solve_dual_kernel<double, 32, false, 2, 4, true>"),
-    ("dtrsm k=32 strided, side L forward", r"tri_solve_dual_kernel<double, 32, true, 0, 2, true>"),
-    ("strsm k=32 strided, side L forward", r"tri_solve_small_kernel<float, 32, true, 0, 4, true>"),
+    ("dtrsm k=32 strided, side L forward (config 3, 16-byte accesses)", r"tri_left_vec_kernel<double, 32, 0, 2, 6>"),
+    ("strsm k=32 strided, side L forward (config 3, 16-byte accesses)", r"tri_left_vec_kernel<float, 32, 0, 4, 6>"),
+    ("dtrsm k=32 side L forward, element-wise fallback (pointer array / unaligned)", r"tri_solve_dual_kernel<double, 32, true, 0, 2, false>"),
+    ("dtrsm k=32 strided, side R backward, one vector per lane", r"tri_right_vec_kernel<double, 32, 1, 4, 4>"),
     ("dpotrf n>32 pointer array (config 4)", r"potrf_panel_mma_kernel<double, 32, false>"),
     ("spotrf n>32 pointer array", r"potrf_panel_mma_kernel<float, 32, false>"),
-    ("dposv solve n>32, 16 rhs rows, pointer array", r"tri_solve_blocked_kernel<double, false, 2, 16, 4, false>"),
+    ("dposv solve n>32, 16 rhs rows, pointer array (config 4, DMMA)", r"tri_solve_mma_kernel<2, 16, 4, false>"),
+    ("sposv solve n>32, 16 rhs rows, pointer array (FMA)", r"tri_solve_blocked_kernel<float, false, 2, 16, 4, false>"),
+    ("lauum n>32 (blocked, in place)", r"lauum_blocked_kernel<double, 4, true>"),
+    ("non-uniform dtrsm, side R forward", r"tri_solve_nonuniform_kernel<double, false, true>"),
     ("dpptrf n=32 packed (TMA in + out)", r"potrf_packed_kernel<double, 32, 8, 1, true, true, true, false>"),
     ("dpptrf n=8 packed (lane per matrix)", r"potrf_packed_lane_kernel<double, 8, 4, 4>"),
     ("dpotrf 32<n<=256 smem-resident (opt-in)", r"potrf_smem_kernel<8, 1, false>"),
