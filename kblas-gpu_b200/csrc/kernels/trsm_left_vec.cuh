@@ -111,7 +111,7 @@ __device__ __forceinline__ void tri_vec_substitute(T (&x)[NP], const T *Ls, cons
 template <typename T, int NP, int OP, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 tri_left_vec_kernel(const int k, const int vec, const T alpha, const T *__restrict__ A0, const int lda, const long strideA,
-                    T *__restrict__ B0, const int ldb, const long strideB, const int batchCount, const int slabs) {
+                    T *__restrict__ B0, const int ldb, const long strideB, const int batchCount, const int slabs, const int ahead) {
   constexpr int VW = TriLeftVecSmem<T, NP>::VW;
   constexpr int NV = NP / VW;
   constexpr int TS = TriLeftVecSmem<T, NP>::TS;
@@ -141,6 +141,13 @@ tri_left_vec_kernel(const int k, const int vec, const T alpha, const T *__restri
   for (int i0 = 0; i0 < 32 * NV; i0 += 32) {
     const int i = i0 + lane, c = i / NV, r0 = (i % NV) * VW;
     cp_async16_if(tile + c * TS + r0, B + (long)c * ldb + r0, c < ncol && r0 < k);
+  }
+  if (ahead > 0) {  // the operands of the task a later CTA will own: into L2 (see prefetch_solve_task_l2)
+    const long ptask = task + (long)ahead * WARPS;
+    if (ptask < (long)batchCount * slabs) {
+      const long pmat = ptask / slabs;
+      prefetch_solve_task_l2<T, NP, true>(A0 + pmat * strideA, lda, B0 + pmat * strideB, ldb, (int)(ptask % slabs) * 32, vec, lane, 32);
+    }
   }
   cp_async_wait_all();
   __syncwarp();
@@ -192,7 +199,7 @@ struct TriRightVecSmem {
 template <typename T, int NP, int OP, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 tri_right_vec_kernel(const int k, const int vec, const T alpha, const T *__restrict__ A0, const int lda, const long strideA,
-                     T *__restrict__ B0, const int ldb, const long strideB, const int batchCount, const int slabs) {
+                     T *__restrict__ B0, const int ldb, const long strideB, const int batchCount, const int slabs, const int ahead) {
   constexpr int VW = 16 / (int)sizeof(T);
   constexpr int NV = NP / VW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,6 +226,13 @@ tri_right_vec_kernel(const int k, const int vec, const T alpha, const T *__restr
   for (int j = 0; j < NP; ++j) {
     x[j] = T(0);
     ldg_stream_if(x[j], B + my + (long)j * ldb, my < vec && j < k);
+  }
+  if (ahead > 0) {
+    const long ptask = task + (long)ahead * WARPS;
+    if (ptask < (long)batchCount * slabs) {
+      const long pmat = ptask / slabs;
+      prefetch_solve_task_l2<T, NP, false>(A0 + pmat * strideA, lda, B0 + pmat * strideB, ldb, (int)(ptask % slabs) * 32, vec, lane, 32);
+    }
   }
   cp_async_wait_all();
   __syncwarp();

@@ -42,7 +42,10 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
   auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
-  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs);
+  // CTAs resident on the whole GPU = how far ahead the kernel prefetches into L2 (variant 46: no prefetch, A/B)
+  const bool pf = h->variant_override != 46 && (NP > 16 || sizeof(T) == 4);  // measured: see prefetch_solve_task_l2
+  const int ahead = pf ? h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, 2) : 0;
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(vec, alpha, A, lda, B, ldb, batchCount, slabs, ahead);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -68,7 +71,9 @@ static int launch_tri_left_vec(KBlasHandle *h, const char *name, int k, int vec,
   const size_t smem = (size_t)WARPS * TriLeftVecSmem<T, NP>::per_warp * sizeof(T);
   auto kern = tri_left_vec_kernel<T, NP, OP, WARPS, MINB>;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
-  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs);
+  const int ahead = h->variant_override == 46 ? 0 : h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, MINB);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs,
+                                                        ahead);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
@@ -97,7 +102,9 @@ static int launch_tri_right_vec(KBlasHandle *h, const char *name, int k, int vec
   const size_t smem = (size_t)WARPS * TriRightVecSmem<T, NP>::per_warp * sizeof(T);
   auto kern = tri_right_vec_kernel<T, NP, OP, WARPS, MINB>;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
-  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs);
+  const int ahead = h->variant_override == 46 ? 0 : h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, smem, MINB);
+  kern<<<(unsigned)grid, WARPS * 32, smem, h->stream>>>(k, vec, alpha, A.base, lda, A.stride, B.base, ldb, B.stride, batchCount, slabs,
+                                                        ahead);
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
