@@ -22,7 +22,7 @@ namespace kblasx {
 template <typename T, int NP, int GP, bool LEFT, int OP, int WARPS, bool STRIDED>
 __global__ void __launch_bounds__(WARPS * 32, OP == TRI_BOTH ? 1 : (sizeof(T) * NP > 64 ? 24 : 32) / WARPS)  // <= 80 / 64 registers
 tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
-                     BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount) {
+                     BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int ahead) {
   static_assert(NP <= GP, "one lane per factor row");
   constexpr int MPW = 32 / GP;  // problems per warp
   const int lane = threadIdx.x & 31;
@@ -54,6 +54,19 @@ tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T
   for (int c = 0; c < NC; ++c) {
     t[c] = T(0);
     ldg_stream_if(t[c], B + (long)lg + (long)c * ldb, hrow && c < ncol);
+  }
+  if (ahead > 0) {
+    // the matrix that the same lane group of a later CTA will own: its factor and its B into L2 (hints; one column per lane)
+    const long pmat = mat + (long)ahead * WARPS * MPW;
+    if (pmat < (long)batchCount && lg < (k > ncol ? k : ncol)) {
+      constexpr int ES = (int)sizeof(T);
+      const char *pa = reinterpret_cast<const char *>(Aref.at(pmat)) + (long)lg * lda * ES;
+      const char *pb = reinterpret_cast<const char *>(Bref.at(pmat)) + (long)lg * ldb * ES;
+      if (lg < k)
+        for (int off = 0; off < k * ES; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
+      if (lg < ncol)
+        for (int off = 0; off < nrow * ES; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+    }
   }
   sched_fence();
 
