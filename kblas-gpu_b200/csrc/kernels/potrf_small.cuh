@@ -35,6 +35,17 @@
 
 namespace kblasx {
 
+// 16-byte shared-memory broadcast vector: 2 doubles / 4 floats
+template <typename T> struct BcastVec;
+template <> struct BcastVec<double> {
+  typedef double2 type;
+  static __device__ __forceinline__ double get(const double2 &v, int h) { return h ? v.y : v.x; }
+};
+template <> struct BcastVec<float> {
+  typedef float4 type;
+  static __device__ __forceinline__ float get(const float4 &v, int h) { return h == 0 ? v.x : h == 1 ? v.y : h == 2 ? v.z : v.w; }
+};
+
 // L2 prefetch of the lower triangle of one matrix: lane = column, the 128-byte lines spanning rows
 // [col, n) of that column (DRAM reads are line granular on B200, profiles/r01_dram_granularity.md).
 template <typename T>
@@ -63,11 +74,13 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
   constexpr int MPW = 32 / G;                  // matrices per warp
   constexpr int GH = (16 / G) > 0 ? (16 / G) : 1;  // lane groups per half-warp
   constexpr int SE = SectorElems<T>::value;
-  // broadcast line of one buffer: [group / GH][row pair][group % GH][2]  -- the 16 lanes of a
-  // half-warp write 128 contiguous bytes (conflict-free STS.64), a group reads 16-byte pairs
-  constexpr int PAIR = GH * 2;
-  constexpr int BUF_STRIDE = (NP / 2) * MPW * 2;  // elements per buffer
-  typedef typename Vec2T<T>::type V2;
+  // broadcast line of one buffer: [group / GH][row vector][group % GH][VB]  -- the 16 lanes of a half-warp write
+  // contiguous bytes (conflict-free stores), a group reads 16-byte vectors: VB = 2 doubles / 4 floats per LDS.128
+  // (fp32 with 8-byte pairs kept the shared-memory pipe 90 % busy on n = 32, profiles/r02_ncu_spotrf32_potrf_reg.json)
+  constexpr int VB = 16 / (int)sizeof(T);
+  constexpr int PAIR = GH * VB;
+  constexpr int BUF_STRIDE = (NP / VB) * MPW * VB;  // elements per buffer
+  static_assert(NP % VB == 0, "whole broadcast vectors");
   static_assert(NP % G == 0 && G % 2 == 0 && 32 % G == 0, "bad tiling");
 
   __shared__ __align__(16) T bc[WARPS * 2 * BUF_STRIDE];
@@ -83,7 +96,7 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
   const int warp = threadIdx.x >> 5;
   const int l = lane % G;
   const int g = lane / G;
-  T *const wbase = bc + warp * (2 * BUF_STRIDE) + (g / GH) * ((NP / 2) * PAIR) + (g % GH) * 2;
+  T *const wbase = bc + warp * (2 * BUF_STRIDE) + (g / GH) * ((NP / VB) * PAIR) + (g % GH) * VB;
 
   // persistent CTAs: CTA-batch cb covers warp-batches [cb*WARPS, cb*WARPS + WARPS), a warp-batch
   // covers matrices [wb*MPW, wb*MPW + MPW)
@@ -168,7 +181,7 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
         for (int s = t; s < S; ++s) {
           if (G * s + G - 1 > j) {
             const int k = G * s + l;
-            wbuf[(k >> 1) * PAIR + (k & 1)] = a[KX_IDX(s, j)];
+            wbuf[(k / VB) * PAIR + (k % VB)] = a[KX_IDX(s, j)];
           }
         }
         __syncwarp();
@@ -177,13 +190,13 @@ potrf_reg_kernel(const int n_arg, BatchRef<T, STRIDED> Aref, const int lda, cons
         // or read (like the reference's unguarded register updates); the EXACT kernel stores the
         // saved original bits for them, the generic one does not store them at all.
 #pragma unroll
-        for (int p = (j + 1) / 2; p < NP / 2; ++p) {
-          const V2 v2 = *reinterpret_cast<const V2 *>(wbuf + p * PAIR);
+        for (int p = (j + 1) / VB; p < NP / VB; ++p) {
+          const typename BcastVec<T>::type vv = *reinterpret_cast<const typename BcastVec<T>::type *>(wbuf + p * PAIR);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = 2 * p + h;
+          for (int h = 0; h < VB; ++h) {
+            const int k = VB * p + h;
             if (k > j) {
-              const T v = h ? v2.y : v2.x;
+              const T v = BcastVec<T>::get(vv, h);
 #pragma unroll
               for (int s = k / G; s < S; ++s) a[KX_IDX(s, k)] = fma_t(-a[KX_IDX(s, j)], v, a[KX_IDX(s, k)]);
             }
