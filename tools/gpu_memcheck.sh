@@ -2,7 +2,7 @@
 # compute-sanitizer over the small-batch GPU parity tests of every kernel family: memcheck (out-of-bounds / misaligned
 # accesses, including the TMA bulk copies of the packed kernels) and racecheck (shared-memory hazards of the staged kernels)
 mkdir -p gpurun_out/sanitize
-K="potrf_strided_vs_oracle or pointer_array_shuffled or strided_large_n or large_n_kernel_variants or trsm_strided_vs_oracle or trsm_large_k or trsm_pointer_array_default or potrs_posv_pointer_array_default or potrs_and_posv or posv_pointer_array or left_side or one_vector or host_pipeline or pointer_and_value_helpers"
+K="potrf_strided_vs_oracle or pointer_array_shuffled or strided_large_n or large_n_kernel_variants or trsm_strided_vs_oracle or trsm_large_k or trsm_pointer_array_default or potrs_posv_pointer_array_default or potrs_and_posv or posv_pointer_array or left_side or one_vector or upper_and_unit or nonuniform or host_pipeline or pointer_and_value_helpers"
 timeout 2400 compute-sanitizer --tool memcheck --launch-timeout 120 --error-exitcode 9 --print-limit 20 \
   python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "$K" > gpurun_out/sanitize/memcheck_parity.log 2>&1
 echo "memcheck parity exit $?"; grep -E "passed|failed|ERROR SUMMARY" gpurun_out/sanitize/memcheck_parity.log | tail -3
