@@ -19,7 +19,11 @@
 
 namespace kblasx {
 
-template <typename T, int NP, int GP, bool LEFT, int OP, int WARPS, bool STRIDED>
+// FULL: k == NP and every lane of a group owns a row (side R: vec == GP; side L: NP == GP == vec) -- no bounds predicates
+// at all.  These kernels are issue-bound (one warp = 4 problems of 8 x 8 is ~500 instructions for 34 FMAs per lane), so
+// every predicate and 64-bit address multiply that goes away shows up in the time; the unmodified reference was 4-14 %
+// faster on fp32 n = 8 with the generic form (profiles/r02_ours_vs_reference.txt).
+template <typename T, int NP, int GP, bool LEFT, int OP, int WARPS, bool STRIDED, bool FULL = false>
 __global__ void __launch_bounds__(WARPS * 32, OP == TRI_BOTH ? 1 : (sizeof(T) * NP > 64 ? 24 : 32) / WARPS)  // <= 80 / 64 registers
 tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda,
                      BatchRef<T, STRIDED> Bref, const int ldb, const int batchCount, const int ahead) {
@@ -39,33 +43,54 @@ tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T
   T *tile = tiles + (LEFT ? (warp * MPW + g) * GP * (NP + 1) : 0);
 
   // ---- every global load up front: my row of the factor, my row of B -------------------------------
+  constexpr int SE = SectorElems<T>::value;
   T a[NP];
-#pragma unroll
-  for (int c = 0; c < NP; ++c) {
-    a[c] = (c == lg) ? T(1) : T(0);  // identity padding for k < NP
-    ldg_stream_if(a[c], A + (long)lg + (long)c * lda, lg < k && c < k && c <= lg);
-  }
   const int nrow = LEFT ? k : vec;  // rows / columns of B
   const int ncol = LEFT ? vec : k;
-  const bool hrow = live && (lg < nrow);
+  const bool hrow = FULL ? live : (live && (lg < nrow));
   constexpr int NC = LEFT ? GP : NP;
   T t[NC];
+  if (FULL) {
+    // whole sectors of my factor row (entries above the diagonal are never used), my whole row of B; column pointers advance
+    // by the leading dimension instead of a 64-bit multiply per element
+    const T *pa = A + lg;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    t[c] = T(0);
-    ldg_stream_if(t[c], B + (long)lg + (long)c * ldb, hrow && c < ncol);
+    for (int c = 0; c < NP; ++c) {
+      a[c] = T(0);
+      if (NP <= SE) a[c] = ldg_stream(pa);
+      else ldg_stream_if(a[c], pa, (lg | (SE - 1)) >= c);
+      pa += lda;
+    }
+    const T *pb = B + lg;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      t[c] = ldg_stream(pb);
+      pb += ldb;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+      a[c] = (c == lg) ? T(1) : T(0);  // identity padding for k < NP
+      ldg_stream_if(a[c], A + (long)lg + (long)c * lda, lg < k && c < k && c <= lg);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      t[c] = T(0);
+      ldg_stream_if(t[c], B + (long)lg + (long)c * ldb, hrow && c < ncol);
+    }
   }
   if (ahead > 0) {
-    // the matrix that the same lane group of a later CTA will own: its factor and its B into L2 (hints; one column per lane)
+    // the matrix that the same lane group of a later CTA will own: the lines its factor and its B span, into L2 (hints)
     const long pmat = mat + (long)ahead * WARPS * MPW;
-    if (pmat < (long)batchCount && lg < (k > ncol ? k : ncol)) {
+    if (pmat < (long)batchCount) {
       constexpr int ES = (int)sizeof(T);
-      const char *pa = reinterpret_cast<const char *>(Aref.at(pmat)) + (long)lg * lda * ES;
-      const char *pb = reinterpret_cast<const char *>(Bref.at(pmat)) + (long)lg * ldb * ES;
-      if (lg < k)
-        for (int off = 0; off < k * ES; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
-      if (lg < ncol)
-        for (int off = 0; off < nrow * ES; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+      const char *pa = reinterpret_cast<const char *>(Aref.at(pmat));
+      const char *pb = reinterpret_cast<const char *>(Bref.at(pmat));
+      const int abytes = ((k - 1) * lda + k) * ES, bbytes = ((ncol - 1) * ldb + nrow) * ES;
+#pragma unroll 1
+      for (int off = lg * 128; off < abytes; off += GP * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
+#pragma unroll 1
+      for (int off = lg * 128; off < bbytes; off += GP * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
     }
   }
   sched_fence();
@@ -114,17 +139,23 @@ tri_solve_reg_kernel(const int k, const int vec, const T alpha, BatchRef<const T
 
   T *Bs = launder(B);  // fresh store addresses: the 16 load addresses would otherwise stay live through the solve
   if (!LEFT) {
+    T *ps = Bs + lg;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) stg_stream_if(Bs + (long)lg + (long)j * ldb, x[j], hrow && j < ncol);
+    for (int j = 0; j < NP; ++j) {
+      stg_stream_if(ps, x[j], FULL ? hrow : (hrow && j < ncol));
+      ps += ldb;
+    }
   } else {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < NP; ++j) tile[lg * (NP + 1) + j] = x[j];
     __syncwarp();
+    T *ps = Bs + lg;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const T out = (lg < NP) ? tile[c * (NP + 1) + lg] : T(0);
-      stg_stream_if(Bs + (long)lg + (long)c * ldb, out, hrow && c < ncol);
+      stg_stream_if(ps, out, FULL ? hrow : (hrow && c < ncol));
+      ps += ldb;
     }
   }
 }

@@ -121,9 +121,16 @@ static int launch_tri_reg(KBlasHandle *h, const char *name, int k, int vec, T al
   constexpr int WARPS = 4, MPW = 32 / GP;
   const long wtasks = ((long)batchCount + MPW - 1) / MPW;
   const long grid = (wtasks + WARPS - 1) / WARPS;
-  auto kern = tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED>;
-  const int ahead = h->variant_override == 46 ? 0 : h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, 0, 4);
-  kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, ahead);
+  const bool full = k == NP && vec == GP && (!LEFT || NP == GP);
+  if (full) {
+    auto kern = tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED, true>;
+    const int ahead = h->variant_override == 46 ? 0 : h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, 0, 4);
+    kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, ahead);
+  } else {
+    auto kern = tri_solve_reg_kernel<T, NP, GP, LEFT, OP, WARPS, STRIDED, false>;
+    const int ahead = h->variant_override == 46 ? 0 : h->sm_count * kx_ctas_per_sm(h, kern, WARPS * 32, 0, 4);
+    kern<<<(unsigned)grid, WARPS * 32, 0, h->stream>>>(k, vec, alpha, A, lda, B, ldb, batchCount, ahead);
+  }
   h->note_launch(name);
   check_error_ret(cudaGetLastError(), KBLAS_UnknownError);
   return KBLAS_Success;
