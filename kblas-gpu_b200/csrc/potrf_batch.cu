@@ -143,11 +143,11 @@ int potrf_batch_core(KBlasHandle *h, char uplo, int n, BatchRef<T, STRIDED> A, i
     }
     if (n <= 0) return KBLAS_Success;
     check_ret_error((transpose_inplace<T, STRIDED>(h, n, A, lda, batchCount)));
-    check_ret_error((potrf_batch_core<T, STRIDED>(h, KBLAS_Lower, n, A, lda, batchCount, info)));
+    const int rc = potrf_batch_core<T, STRIDED>(h, KBLAS_Lower, n, A, lda, batchCount, info);
     const char *factor_kernel = h->last_kernel;
-    check_ret_error((transpose_inplace<T, STRIDED>(h, n, A, lda, batchCount)));
+    const int rc2 = transpose_inplace<T, STRIDED>(h, n, A, lda, batchCount);  // also after a failed launch: A goes back to its layout
     h->last_kernel = factor_kernel;
-    return KBLAS_Success;
+    return rc != KBLAS_Success ? rc : rc2;
   }
   if (batchCount <= 0) {
     // reference: grid.x == 0 -> launch error -> KBLAS_UnknownError (drivers.cuh:82-88)
