@@ -21,16 +21,9 @@
 
 #include "common.cuh"
 #include "trsm_small.cuh"  // TriOp, sched_fence
+#include "vec16.cuh"
 
 namespace kblasx {
-
-__device__ __forceinline__ void lds_vec(double (&v)[2], const double *p) {
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"((unsigned)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void lds_vec(float (&v)[4], const float *p) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"((unsigned)__cvta_generic_to_shared(p)));
-}
 
 // L2 prefetch of everything one (matrix, 32-vector slab) task of a k <= NP solve reads: the lower part of the factor columns
 // and the slab of B (side R: 32 rows of NP columns, side L: NP rows of 32 columns).  Hints only, one 128-byte line per
@@ -68,7 +61,8 @@ struct TriDualSmem {
   static constexpr int VW = 16 / (int)sizeof(T);
   static constexpr int per_problem = NP * NP + NP + VW;  // factor + reciprocal diagonal + bank-skew pad
   static constexpr int tile_stride = NP + 1;             // odd: conflict-free transposed reads
-  static constexpr int tile = LEFT ? 32 * tile_stride + (sizeof(T) == 4 ? 16 : 0) : 0;  // side L: 32 vectors x NP entries (+ bank skew between the two problems, fp32)
+  static constexpr int tile_stride16 = NP + VW;          // 16-byte aligned pitch of the VEC16 path (conflict-free LDS.128 / STS.128)
+  static constexpr int tile = LEFT ? 32 * tile_stride16 + (sizeof(T) == 4 ? 16 : 0) : 0;  // side L: 32 vectors x NP entries (+ bank skew between the two problems, fp32)
   static constexpr int per_warp = 2 * (per_problem + tile);
   static_assert((per_problem * sizeof(T)) % 16 == 0 && (per_problem * sizeof(T)) % 128 != 0,
                 "the two factor copies of a warp must sit a non-zero multiple of 16 B apart (mod 128)");
@@ -83,7 +77,10 @@ struct TriDualSmem {
 #ifndef KX_DUAL_FENCE32
 #define KX_DUAL_FENCE32 4
 #endif
-template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED>
+// VEC16 (side L only; lda, ldb multiples of 16 bytes, 16-byte aligned operands -- the launcher checks): the slab of B moves
+// global <-> shared as 16-byte chunks (cp.async in, LDS.128 + streaming STG.128 out) and a lane reads / writes its two
+// columns with 128-bit shared accesses, instead of one 4- or 8-byte LDG / STS / LDS / STG per element each way.
+template <typename T, int NP, bool LEFT, int OP, int WARPS, bool STRIDED, bool VEC16 = false>
 __global__ void __launch_bounds__(WARPS * 32, (sizeof(T) == 8 ? KX_DUAL_MINB64 : (NP > 24 ? 3 : 4)) * 4 / WARPS)
 tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> Aref, const int lda, BatchRef<T, STRIDED> Bref,
                       const int ldb, const int batchCount, const int slabs, const int ahead) {
@@ -131,6 +128,15 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
       ldg_stream_if(x0[j], B + my0 + (long)j * ldb, h0);
       ldg_stream_if(x1[j], B + my1 + (long)j * ldb, h1);
     }
+  } else if (VEC16) {
+    constexpr int TSV = TriDualSmem<T, NP, LEFT>::tile_stride16;
+    const T *Bv = B + (long)v0 * ldb;
+    const int ncol = !live ? 0 : ((vec - v0 < 32) ? (vec - v0) : 32);
+#pragma unroll
+    for (int i0 = 0; i0 < 32 * NV; i0 += 16) {
+      const int i = i0 + lg, c = i / NV, r0 = (i % NV) * VW;
+      cp_async16_if(tile + c * TSV + r0, Bv + (long)c * ldb + r0, c < ncol);
+    }
   } else {
     // side L: vector = column of B.  Lane lg reads rows lg and lg+16 of 16 columns at a time (coalesced) and
     // parks them in the tile as tile[column][row]; the vectors are then read back along the rows.
@@ -170,6 +176,20 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
   }
   cp_async_wait_all();
   __syncwarp();
+  if (LEFT && VEC16) {  // my two columns of the slab = rows lg and lg + 16 of the tile
+    constexpr int TSV = TriDualSmem<T, NP, LEFT>::tile_stride16;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      T c0[VW], c1[VW];
+      lds_vec(c0, tile + lg * TSV + q * VW);
+      lds_vec(c1, tile + (lg + 16) * TSV + q * VW);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        x0[q * VW + e] = c0[e];
+        x1[q * VW + e] = c1[e];
+      }
+    }
+  }
   // reciprocal diagonal: one division per lane and diagonal entry
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -236,6 +256,32 @@ tri_solve_dual_kernel(const int vec, const T alpha, BatchRef<const T, STRIDED> A
     for (int j = 0; j < NP; ++j) {
       stg_stream_if(Bs + my0 + (long)j * ldb, x0[j], h0);
       stg_stream_if(Bs + my1 + (long)j * ldb, x1[j], h1);
+    }
+  } else if (VEC16) {
+    constexpr int TSV = TriDualSmem<T, NP, LEFT>::tile_stride16;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      T c0[VW], c1[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        c0[e] = x0[q * VW + e];
+        c1[e] = x1[q * VW + e];
+      }
+      sts_vec(tile + lg * TSV + q * VW, c0);
+      sts_vec(tile + (lg + 16) * TSV + q * VW, c1);
+    }
+    __syncwarp();
+    T *Bv = Bs + (long)v0 * ldb;
+    const int ncol = !live ? 0 : ((vec - v0 < 32) ? (vec - v0) : 32);
+#pragma unroll
+    for (int i0 = 0; i0 < 32 * NV; i0 += 16) {
+      const int i = i0 + lg, c = i / NV, r0 = (i % NV) * VW;
+      if (c < ncol) {
+        T o[VW];
+        lds_vec(o, tile + c * TSV + r0);
+        stg_vec_stream(Bv + (long)c * ldb + r0, o);
+      }
     }
   } else {
     __syncwarp();

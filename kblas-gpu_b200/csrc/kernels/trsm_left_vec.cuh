@@ -20,28 +20,10 @@
 
 #include "common.cuh"
 #include "trsm_small.cuh"  // sched_fence
-#include "trsm_dual.cuh"   // lds_vec
+#include "vec16.cuh"
+#include "trsm_dual.cuh"   // prefetch_solve_task_l2
 
 namespace kblasx {
-
-__device__ __forceinline__ void cp_async16_if(void *smem_dst, const void *gsrc, bool pred) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
-               "r"(pred ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void sts_vec(double *p, const double (&v)[2]) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v[0]), "d"(v[1]) : "memory");
-}
-__device__ __forceinline__ void sts_vec(float *p, const float (&v)[4]) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v[0]), "f"(v[1]),
-               "f"(v[2]), "f"(v[3]) : "memory");
-}
-__device__ __forceinline__ void stg_vec_stream(double *p, const double (&v)[2]) {
-  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
-}
-__device__ __forceinline__ void stg_vec_stream(float *p, const float (&v)[4]) {
-  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
-               : "memory");
-}
 
 #ifndef KX_TLV_FENCE_F64
 #define KX_TLV_FENCE_F64 2

@@ -32,7 +32,7 @@ static int launch_tri_small(KBlasHandle *h, const char *name, int k, int vec, T 
 }
 
 // full NP x NP factor: two vectors per lane, two problems per warp, cp.async staging (kernels/trsm_dual.cuh)
-template <typename T, int NP, bool LEFT, int OP, bool STRIDED>
+template <typename T, int NP, bool LEFT, int OP, bool STRIDED, bool VEC16 = false>
 static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, BatchRef<const T, STRIDED> A, int lda,
                            BatchRef<T, STRIDED> B, int ldb, int batchCount) {
   constexpr int WARPS = LEFT ? 2 : 4;  // side L carries a transpose tile per problem: 2-warp CTAs keep 3 CTAs per SM
@@ -40,7 +40,7 @@ static int launch_tri_dual(KBlasHandle *h, const char *name, int vec, T alpha, B
   const long tasks = (long)batchCount * slabs;
   const long grid = (tasks + 2 * WARPS - 1) / (2 * WARPS);
   const size_t smem = (size_t)WARPS * TriDualSmem<T, NP, LEFT>::per_warp * sizeof(T);
-  auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED>;
+  auto kern = tri_solve_dual_kernel<T, NP, LEFT, OP, WARPS, STRIDED, VEC16>;
   check_error_ret(kx_allow_smem(h, kern, smem), KBLAS_CUDA_Error);
   // CTAs resident on the whole GPU = how far ahead the kernel prefetches into L2 (variant 46: no prefetch, A/B)
   const bool pf = h->variant_override != 46 && (NP > 16 || sizeof(T) == 4);  // measured: see prefetch_solve_task_l2
@@ -222,6 +222,17 @@ static int tri_small_np(KBlasHandle *h, int k, int vec, T alpha, BatchRef<const 
     //   k=16: only the fused potrs wins (16 vectors: fp64 1.59 vs 2.54, fp32 0.91 vs 1.49); k=8 and few vectors (idle
     //   lanes) stay on the register kernels.  Variant 40 forces it wherever it is eligible, 41 switches it off.
     const int vo = h->variant_override;
+    if constexpr (OP == TRI_BOTH && STRIDED) {
+      // fused side-L potrs, k = 24 / 32: two vectors per lane (half the factor broadcasts of the one-vector kernel, which is
+      // bound by the shared-memory pipe here) with the slab of B staged in 16-byte chunks.  Measured (B200, 2^20 problems, ms,
+      // against what it replaces): fp64 k = 24 3.79 vs 4.21, fp32 k = 32 2.80 vs 3.26, k = 24 1.92 vs 2.03; fp64 k = 32 6.47 vs
+      // 6.28 -- 34 KB of shared memory per warp leave 6 warps per SM there, so that one stays on the one-vector kernel.
+      // Variant 53 switches it off.
+      if ((k == 24 || (k == 32 && sizeof(T) == 4)) && vec > 16 && vo != 53 && vo != 40 && vo != 41 && tri_left_vec_ok<T>(k, A, lda, B, ldb)) {
+        if (k == 24) return launch_tri_dual<T, 24, LEFT, OP, STRIDED, true>(h, "tri_dual16<NP=24>", vec, alpha, A, lda, B, ldb, batchCount);
+        return launch_tri_dual<T, 32, LEFT, OP, STRIDED, true>(h, "tri_dual16<NP=32>", vec, alpha, A, lda, B, ldb, batchCount);
+      }
+    }
     const bool pays = k > 16 ? (vec > 16 && !(sizeof(T) == 8 && OP == TRI_BOTH && k <= 24)) : (k > 8 && vec > 8 && OP == TRI_BOTH);
     const bool want = vo == 40 || (vo != 41 && pays);
     if (want && tri_left_vec_ok<T>(k, A, lda, B, ldb)) {
