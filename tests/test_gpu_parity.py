@@ -602,6 +602,34 @@ def test_trsm_nonuniform_batch(env, p, side, uplo, trans, diag):
         assert np.abs(X - want).max() <= 100 * max(k, 1) * eps * max(1.0, np.abs(want).max()), (b, m, n)
 
 
+@pytest.mark.parametrize("p,k", [("D", 24), ("S", 24), ("S", 32)])
+@pytest.mark.parametrize("vec,pad", [(32, 0), (40, 1), (17, 2)])
+def test_potrs_left_two_vector_16_byte_kernel(env, p, k, vec, pad):
+    """fused side-L potrs on the two-vector kernel with 16-byte staging (tri_dual16: k = 24, and k = 32 in fp32, aligned strided
+    operands, more than 16 right-hand sides) -- the default for those shapes; against the oracle's trsm L,L,N + L,L,T."""
+    kb, h, torch = env
+    dt = DT[p]
+    vw = 16 // np.dtype(dt).itemsize
+    batch = 43
+    lda, ldb = k + pad * vw, k + 2 * pad * vw
+    A = U.rand_spd_batch(batch, k, lda=lda, dtype=dt, seed=k + 21)
+    assert U.oracle_potrf(A, k) == 1
+    B0 = U.rand_batch(batch, k, vec, ld=ldb, dtype=dt, seed=k * 10 + vec)
+    Bo = B0.copy()
+    U.oracle_trsm("L", "L", "N", "N", k, vec, 1.0, A, Bo)
+    U.oracle_trsm("L", "L", "T", "N", k, vec, 1.0, A, Bo)
+    dA, dB = _dev(torch, A), _dev(torch, B0)
+    h.potrs_batch_strided_wsquery(k, vec, batch)
+    h.allocate_workspace()
+    assert h.potrs_batch_strided("L", "L", k, vec, dA, lda, k * lda, dB, ldb, vec * ldb, batch) == kb.KBLAS_Success
+    torch.cuda.synchronize()
+    assert h.last_kernel.startswith("tri_dual16"), h.last_kernel
+    got = dB.cpu().numpy()
+    assert np.abs(got[:, :, :k] - Bo[:, :, :k]).max() <= 100 * k * U.EPS[dt] * max(1.0, np.abs(Bo[:, :, :k]).max())
+    assert np.array_equal(got[:, :, k:], B0[:, :, k:]), "ldb padding untouched"
+    assert np.array_equal(dA.cpu().numpy(), A), "the factor is read-only"
+
+
 def _slack_copy(torch, a, off):
     """device copy of numpy array `a` with `off` elements of slack in front (and 4 behind): every matrix then starts
     `off` elements past a 16-byte boundary -- with off = 1 the pointers are element-aligned but NOT 16-byte aligned"""
