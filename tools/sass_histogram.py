@@ -15,7 +15,7 @@ LIB = os.path.join(ROOT, "kblas-gpu_b200", "lib", "libkblas-gpu.so")
 # (label, regex on the demangled kernel name): the default dispatch of every BASELINE configuration
 WANT = [
     ("dpotrf n=32 strided (headline)", r"potrf_reg_kernel<double, 32, 8, 8, 1, true, true, true>"),
-    ("spotrf n=32 strided", r"potrf_reg_kernel<float, 32, 8, 8, 2, true, true, true>"),
+    ("spotrf n=32 strided", r"potrf_reg_kernel<float, 32, 8, 4, 3, true, true, true>"),
     ("dpotrf n=8 strided", r"potrf_reg_kernel<double, 8, 8, 4, 4, true, true, false>"),
     ("dpotrs / dtrsm k=32 strided, side R fused fwd+bwd", r"tri_solve_dual_kernel<double, 32, false, 2, 4, true>"),
     ("dtrsm k=32 strided, side L forward (config 3, 16-byte accesses)", r"tri_left_vec_kernel<double, 32, 0, 2, 6>"),
