@@ -46,12 +46,18 @@ static int potrf_small_dispatch(KBlasHandle *h, int n, BatchRef<T, STRIDED> A, i
   const bool exact = (n % 8 == 0) && (h->info_mode == KBLASX_INFO_COMPAT) && !h->exact_stores;
   constexpr bool F32 = sizeof(T) == 4;
   if (n <= 8) return exact ? KX_LAUNCH_REG(8, 8, 4, 4, true, false) : KX_LAUNCH_REG(8, 8, 4, 4, false, false);
-  if (n <= 16) return exact ? KX_LAUNCH_REG(16, 8, 4, 4, true, true) : KX_LAUNCH_REG(16, 8, 4, 4, false, true);
+  if (n <= 16) {
+    if (!exact) return KX_LAUNCH_REG(16, 8, 4, 4, false, true);
+    // measured (B200, 2^20 matrices, ms): fp64 lockstep 3 / 4 / 6 CTAs per SM 0.572 / 0.587 / 0.672, free-running 0.600;
+    // fp32 lockstep 0.439, free-running 0.419
+    return F32 ? KX_LAUNCH_REG(16, 8, 4, 4, true, false) : KX_LAUNCH_REG(16, 8, 4, 3, true, true);
+  }
   if (n <= 24) {
     if (!exact) return KX_LAUNCH_REG(24, 8, 4, 3, false, true);
     // measured (B200, batch 2^20): fp64 one 8-warp lockstep CTA per SM 0.59 vs 3 x 4 warps 0.52;
     // fp32 the other way round (0.45 vs 0.49)
-    return F32 ? KX_LAUNCH_REG(24, 8, 4, 3, true, true) : KX_LAUNCH_REG(24, 8, 8, 1, true, true);
+    // (round 2, 16-byte broadcast vectors: fp32 3 x 4 warps free-running 0.788 against 0.818 in lockstep; fp64 unchanged)
+    return F32 ? KX_LAUNCH_REG(24, 8, 4, 3, true, false) : KX_LAUNCH_REG(24, 8, 8, 1, true, true);
   }
   if constexpr (F32) {
     // measured (B200, 2^20 matrices, 16-byte broadcast vectors, ms best / mean): 2 x 8 warps (128 registers, 96 B of spills)
